@@ -1,0 +1,266 @@
+// gns_common.cuh — layouts and device helpers shared by the forward and backward kernels.
+//
+// Data layout in shared memory ("grid-interleaved SoA"): every per-bus / per-line /
+// per-generator quantity of the G grids a CTA works on is stored as  [quantity][item][G]
+// with the grid index fastest.  A thread owns one item (bus or line) for VG consecutive
+// grids and moves them with one 4*VG-byte access, so consecutive lanes touch consecutive
+// words (conflict-free) and every warp-uniform weight fetched from shared memory is
+// amortised over VG items.  Buses are stored in the plan's internal order (in-degree
+// descending) so that the lanes of a warp loop over the same number of incoming lines.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gns {
+
+constexpr int kMaxK = 64;
+constexpr float kSlope = 0.01f;  // nn.LeakyReLU default, ref GNS/main.py:23
+
+__host__ __device__ constexpr int pad4(int x) { return (x + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------
+// Packed per-step weight layout.  Every matrix is stored [wide][HP]: the fast index is
+// always the hidden-side index (padded to a multiple of 4 for 128-bit broadcast loads),
+// the slow index the wide side (input of a first layer, output of a last layer).  The
+// same rows serve forward (stream the wide index) and backward (dX and dW^T).
+// Pairing: phi_v feeds L_v, phi_theta feeds L_theta, phi_m feeds L_m (ref GNS/main.py:157-176).
+// ---------------------------------------------------------------------------------
+struct WLayout {
+  int L, H, multi;
+  int HP, PO, POP, LPAD, DIN_L, NPHI;
+  // inside a phi block
+  int phi_w1m, phi_w1f, phi_b1, phi_w2, phi_b2, phi_w4, phi_b4, phi_size;
+  // inside an L-net block
+  int ln_w1, ln_b1, ln_w2, ln_b2, ln_wo, ln_bo_s, ln_bo_m, ln_size_s, ln_size_m;
+  // step block: phi nets in pair order (v, theta, m | single), then L_v, L_theta, L_m
+  int off_phi[3], off_ln[3], wstep;
+};
+
+__host__ __device__ constexpr WLayout make_wlayout(int L, int H, bool multi) {
+  WLayout w{};
+  w.L = L; w.H = H; w.multi = multi ? 1 : 0;
+  w.HP = pad4(H);
+  w.PO = multi ? L : 1;
+  w.POP = pad4(w.PO);
+  w.LPAD = pad4(L);
+  w.DIN_L = 4 + 2 * L;
+  w.NPHI = multi ? 3 : 1;
+  w.phi_w1m = 0;
+  w.phi_w1f = w.phi_w1m + L * w.HP;
+  w.phi_b1 = w.phi_w1f + 5 * w.HP;
+  w.phi_w2 = w.phi_b1 + w.HP;
+  w.phi_b2 = w.phi_w2 + H * w.HP;
+  w.phi_w4 = w.phi_b2 + w.HP;
+  w.phi_b4 = w.phi_w4 + w.PO * w.HP;
+  w.phi_size = w.phi_b4 + w.POP;
+  w.ln_w1 = 0;
+  w.ln_b1 = w.ln_w1 + w.DIN_L * w.HP;
+  w.ln_w2 = w.ln_b1 + w.HP;
+  w.ln_b2 = w.ln_w2 + H * w.HP;
+  w.ln_wo = w.ln_b2 + w.HP;
+  w.ln_bo_s = w.ln_wo + w.HP;
+  w.ln_bo_m = w.ln_wo + L * w.HP;
+  w.ln_size_s = w.ln_bo_s + 4;
+  w.ln_size_m = w.ln_bo_m + w.LPAD;
+  int o = 0;
+  for (int p = 0; p < 3; ++p) { w.off_phi[p] = (p < w.NPHI) ? o : 0; if (p < w.NPHI) o += w.phi_size; }
+  // pair order q: 0 = v, 1 = theta, 2 = m
+  w.off_ln[0] = o; o += w.ln_size_s;
+  w.off_ln[1] = o; o += w.ln_size_s;
+  w.off_ln[2] = o; o += w.ln_size_m;
+  w.wstep = o;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------
+// Topology index block (shared by all grids; copied to shared memory once per CTA).
+// All entries are uint16 (n_bus, n_line < 65536).
+// ---------------------------------------------------------------------------------
+struct TopoOffsets {      // offsets in uint16 units inside the index block
+  int fi, ti;             // [E] internal slot of from / to bus
+  int fa, ta;             // [E] alias line ids: external from / to bus number re-read as a line id
+  int in_ptr, in_ids;     // [N+1], [E] lines entering internal slot n (ascending line id)
+  int out_ptr, out_ids;   // [N+1], [E] lines leaving internal slot n
+  int gen_ptr, gen_ids;   // [N+1], [Gn] generators sitting on internal slot n
+  int ext_of;             // [N] external bus of internal slot
+  int rank_of;            // [N] internal slot of external bus
+  int total;              // padded to a multiple of 8
+};
+
+__host__ __device__ inline TopoOffsets make_topo_offsets(int N, int E, int Gn) {
+  TopoOffsets t{};
+  int o = 0;
+  t.fi = o; o += E;
+  t.ti = o; o += E;
+  t.fa = o; o += E;
+  t.ta = o; o += E;
+  t.in_ptr = o; o += N + 1;
+  t.in_ids = o; o += E;
+  t.out_ptr = o; o += N + 1;
+  t.out_ids = o; o += E;
+  t.gen_ptr = o; o += N + 1;
+  t.gen_ids = o; o += Gn;
+  t.ext_of = o; o += N;
+  t.rank_of = o; o += N;
+  t.total = (o + 7) & ~7;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------
+// Vector-over-grids helpers.
+// ---------------------------------------------------------------------------------
+template <int VG> struct VecIO;
+template <> struct VecIO<1> {
+  __device__ static __forceinline__ void ld(float (&x)[1], const float* p) { x[0] = *p; }
+  __device__ static __forceinline__ void st(float* p, const float (&x)[1]) { *p = x[0]; }
+};
+template <> struct VecIO<2> {
+  __device__ static __forceinline__ void ld(float (&x)[2], const float* p) {
+    float2 t = *reinterpret_cast<const float2*>(p); x[0] = t.x; x[1] = t.y;
+  }
+  __device__ static __forceinline__ void st(float* p, const float (&x)[2]) {
+    *reinterpret_cast<float2*>(p) = make_float2(x[0], x[1]);
+  }
+};
+template <> struct VecIO<4> {
+  __device__ static __forceinline__ void ld(float (&x)[4], const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+  }
+  __device__ static __forceinline__ void st(float* p, const float (&x)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  }
+};
+
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }
+__device__ __forceinline__ float lrelu_grad(float z) { return z > 0.f ? 1.f : kSlope; }
+
+// sin and cos of one float, ~1 ulp: three-constant Cody-Waite reduction by pi/2 with FMAs,
+// then minimax polynomials on [-pi/4, pi/4].  Arguments in this solver are angle
+// differences of a few radians; beyond |x| > 1e5 (where the 3-constant reduction loses
+// bits) the CUDA library routine is called out of line.  Keeping the library's
+// Payne-Hanek slow path out of the persistent kernels' bodies saves registers and ~60 KB of code.
+static __device__ __noinline__ void sincos_slow(float x, float* s, float* c) { sincosf(x, s, c); }
+
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+  if (fabsf(x) > 1.0e5f) { sincos_slow(x, &s, &c); return; }
+  const float q = rintf(x * 0.63661977236758134f);
+  float r = fmaf(q, -1.57079637050628662e+00f, x);
+  r = fmaf(q, 4.37113900018624283e-08f, r);
+  r = fmaf(q, 1.71512449632429490e-15f, r);
+  const int qi = (int)q;
+  const float r2 = r * r;
+  float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, r2, -1.6666654611e-1f);
+  const float sr = fmaf(ps * r2, r, r);
+  float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, r2, 4.166664568298827e-2f);
+  const float cr = fmaf(pc * r2, r2, fmaf(-0.5f, r2, 1.0f));
+  const float s0 = (qi & 1) ? cr : sr;
+  const float c0 = (qi & 1) ? sr : cr;
+  s = (qi & 2) ? -s0 : s0;
+  c = ((qi + 1) & 2) ? -c0 : c0;
+}
+
+// An integer zero the optimiser cannot see through.  Added to a shared-memory weight
+// pointer inside a data-dependent loop it stops loop-invariant code motion from hoisting
+// every weight row of the loop body into registers (and from there into local-memory
+// spills): the rows must be re-read from shared memory as warp-uniform broadcasts.
+__device__ __forceinline__ int opaque_zero() {
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return z;
+}
+
+// Load one padded weight row (HP floats, 16-byte aligned, warp-uniform address).
+template <int HP>
+__device__ __forceinline__ void load_row(float (&w)[HP], const float* row) {
+#pragma unroll
+  for (int c = 0; c < HP / 4; ++c) {
+    float4 t = *reinterpret_cast<const float4*>(row + 4 * c);
+    w[4 * c + 0] = t.x; w[4 * c + 1] = t.y; w[4 * c + 2] = t.z; w[4 * c + 3] = t.w;
+  }
+}
+
+// acc[o][g] += x[g] * row[o]
+template <int H, int HP, int VG>
+__device__ __forceinline__ void row_axpy(float (&acc)[H][VG], const float (&x)[VG], const float* row) {
+  float w[HP];
+  load_row<HP>(w, row);
+#pragma unroll
+  for (int o = 0; o < H; ++o)
+#pragma unroll
+    for (int g = 0; g < VG; ++g) acc[o][g] = fmaf(x[g], w[o], acc[o][g]);
+}
+
+// out[g] = init[g] + sum_o h[o][g] * row[o]
+template <int H, int HP, int VG>
+__device__ __forceinline__ void row_dot(float (&out)[VG], const float (&h)[H][VG], const float* row) {
+  float w[HP];
+  load_row<HP>(w, row);
+#pragma unroll
+  for (int o = 0; o < H; ++o)
+#pragma unroll
+    for (int g = 0; g < VG; ++g) out[g] = fmaf(h[o][g], w[o], out[g]);
+}
+
+// Deterministic per-grid block reduction.  Thread `tid` contributes x[VG] for grids
+// (tid % NGQ)*VG .. +VG.  Requires 32 % NGQ == 0 and blockDim.x % 32 == 0.
+// `red` holds nwarps*G floats.  Every thread receives the total of its own grids.
+template <int VG>
+__device__ __forceinline__ void block_sum_per_grid(float (&x)[VG], float* red, int NGQ) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int G = NGQ * VG;
+  for (int off = 16; off >= NGQ; off >>= 1) {
+#pragma unroll
+    for (int g = 0; g < VG; ++g) x[g] += __shfl_xor_sync(0xffffffffu, x[g], off);
+  }
+  if (lane < NGQ) {
+#pragma unroll
+    for (int g = 0; g < VG; ++g) red[warp * G + lane * VG + g] = x[g];
+  }
+  __syncthreads();
+  const int gq = lane % NGQ;
+#pragma unroll
+  for (int g = 0; g < VG; ++g) x[g] = 0.f;
+  for (int w = 0; w < nwarps; ++w) {
+#pragma unroll
+    for (int g = 0; g < VG; ++g) x[g] += red[w * G + gq * VG + g];
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// Kernel argument blocks
+// ---------------------------------------------------------------------------------
+struct SmemPlan {          // offsets in floats from the start of dynamic shared memory
+  int state;               // [(4+L)][N][G]  v, theta, dP, dQ, m[0..L)
+  int busc;                // [4][N][G]      Pd, Qd, Gs, Bs
+  int genc;                // [6][Gn][G]     Pmax, Pmin, Pset, vg, qg0, Pg0
+  int linef;               // [5][E][G]      r, x, b, tau, shift
+  int yline;               // [N][G]         1/sqrt(r^2+x^2) of lines 0..N-1 (alias lines)
+  int trig;                // [3][N][G]      D, sin D, cos D of lines 0..N-1
+  int flows;               // [4][E][G]      p_from, q_from, p_to, q_to
+  int gsum;                // [4][G]         sum Pd, sum Pset, sum Pmin, sum Pmax
+  int red;                 // [nwarps][G]
+  int weights;             // [wstep]
+  int topo;                // uint16 block (offset in floats)
+  int extra;               // backward-only regions start here
+  int total_floats;
+};
+
+struct FwdArgs {
+  const float* params;     // packed [K][wstep]
+  const float* buses; const float* lines; const float* gens;
+  float* v; float* theta; float* total; float* last;
+  float* ckpt;             // [nbatch][K][(4+L)][N][G] or null
+  float* pglob;            // [nbatch][K][G] or null
+  const uint16_t* topo;    // index block in global memory
+  long long S;
+  int N, E, Gn, K, NGQ, G, nbatch;
+  int need_grad;
+  SmemPlan sm;
+  TopoOffsets to;
+  float wk[kMaxK];         // gamma^(K-k) rounded to float like the reference's python scalar
+};
+
+}  // namespace gns

@@ -1,0 +1,17 @@
+// gns_dispatch.cu — (latent_dim, hidden_dim) -> instantiated kernel launcher.
+#include "gns_host.h"
+namespace gns {
+FwdLauncher find_forward_l10(int multi, int VG, int tmax);
+FwdLauncher find_forward_l20(int multi, int VG, int tmax);
+FwdLauncher find_forward_l64(int multi, int VG, int tmax);
+
+FwdLauncher find_forward(int L, int H, int multi, int VG, int tmax) {
+  if (H != 10) return nullptr;
+  switch (L) {
+    case 10: return find_forward_l10(multi, VG, tmax);
+    case 20: return find_forward_l20(multi, VG, tmax);
+    case 64: return find_forward_l64(multi, VG, tmax);
+  }
+  return nullptr;
+}
+}  // namespace gns

@@ -1,0 +1,530 @@
+// gns_forward.cuh — persistent K-step forward kernel (one CTA = G grids, all K steps).
+//
+// Restates ref GNS/main.py:140-202 (+ :34-104 for the physics) for G grids at a time.
+// Per step and per bus the whole message-passing pipeline runs inside ONE thread:
+//   P   = W1[:, :L] m[n] + b1                       (receiver-only message, quirk Q2)
+//   A   = sum_{lines e into n} lrelu(W2 lrelu(P + W1[:, L:] feat_e) + b2)
+//   S   = W4 A + deg(n) b4                           (= scatter_add of phi outputs, by linearity)
+//   out = L_net([v, theta, dP, dQ, m, S])
+// so the bus aggregation needs neither atomics nor a barrier; the lines entering a bus are
+// walked through the plan's CSR in ascending line order (the reference's scatter order).
+// Then, after one barrier, the Kirchhoff physics runs per line and per bus.
+#pragma once
+#include "gns_common.cuh"
+
+namespace gns {
+
+// ---- staged input load: reference AoS rows -> grid-interleaved SoA in shared memory ----
+// src: [S][rows][cols]; keeps columns c0..cols-1 as dst[(c-c0)][slot(row)][G] (+gl).
+__device__ __forceinline__ void load_block(const float* __restrict__ src, float* __restrict__ dst,
+                                           long long g0, long long S, int G, int rows, int cols, int c0,
+                                           const uint16_t* __restrict__ slot_of_row) {
+  const int per_grid = rows * cols;
+  const int total = per_grid * G;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int gl = idx / per_grid;
+    const int rem = idx - gl * per_grid;
+    const int row = rem / cols;
+    const int c = rem - row * cols;
+    long long g = g0 + gl;
+    if (g >= S) g = S - 1;  // tail batch: replicate the last grid (results are not stored)
+    const float val = __ldg(src + g * per_grid + rem);
+    if (c >= c0) {
+      const int slot = slot_of_row ? (int)slot_of_row[row] : row;
+      dst[((c - c0) * rows + slot) * G + gl] = val;
+    }
+  }
+}
+
+template <int L, int H, bool MULTI, int VG, int TMAX>
+__global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
+  constexpr WLayout W = make_wlayout(L, H, MULTI);
+  constexpr int HP = pad4(H);
+  constexpr int PO = MULTI ? L : 1;
+  using IO = VecIO<VG>;
+
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, E = a.E, Gn = a.Gn, G = a.G, NGQ = a.NGQ, K = a.K;
+  const int NG = N * G, EG = E * G, GnG = Gn * G;
+  float* const s_state = smem + a.sm.state;
+  float* const s_busc = smem + a.sm.busc;
+  float* const s_genc = smem + a.sm.genc;
+  float* const s_linef = smem + a.sm.linef;
+  float* const s_y = smem + a.sm.yline;
+  float* const s_trig = smem + a.sm.trig;
+  float* const s_flow = smem + a.sm.flows;
+  float* const s_gsum = smem + a.sm.gsum;
+  float* const s_red = smem + a.sm.red;
+  float* const s_w = smem + a.sm.weights;
+  uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
+
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int slot = tid / NGQ;           // bus slot (internal order) in bus phases
+  const int gq = tid - slot * NGQ;
+  const int gcol = gq * VG;
+  const bool bus_on = slot < N;
+
+  // topology indices: once per CTA
+  for (int i = tid; i < a.to.total / 2; i += T)
+    reinterpret_cast<uint32_t*>(s_topo)[i] = reinterpret_cast<const uint32_t*>(a.topo)[i];
+  const uint16_t* const t_fi = s_topo + a.to.fi;
+  const uint16_t* const t_ti = s_topo + a.to.ti;
+  const uint16_t* const t_fa = s_topo + a.to.fa;
+  const uint16_t* const t_ta = s_topo + a.to.ta;
+  const uint16_t* const t_inp = s_topo + a.to.in_ptr;
+  const uint16_t* const t_ini = s_topo + a.to.in_ids;
+  const uint16_t* const t_outp = s_topo + a.to.out_ptr;
+  const uint16_t* const t_outi = s_topo + a.to.out_ids;
+  const uint16_t* const t_genp = s_topo + a.to.gen_ptr;
+  const uint16_t* const t_geni = s_topo + a.to.gen_ids;
+  const uint16_t* const t_ext = s_topo + a.to.ext_of;
+  const uint16_t* const t_rank = s_topo + a.to.rank_of;
+  __syncthreads();
+
+  for (int batch = blockIdx.x; batch < a.nbatch; batch += gridDim.x) {
+    const long long g0 = (long long)batch * G;
+
+    // ---------------- load + de-interleave the G grids of this batch ----------------
+    load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, t_rank);
+    load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, nullptr);
+    load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, nullptr);
+    __syncthreads();
+
+    // ---------------- state init (ref GNS/main.py:141-152) ----------------
+    int e_in0 = 0, e_in1 = 0, e_out0 = 0, e_out1 = 0, j0 = 0, j1 = 0;
+    float part4[4][VG];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int g = 0; g < VG; ++g) part4[q][g] = 0.f;
+    if (bus_on) {
+      const int n = slot;
+      e_in0 = t_inp[n]; e_in1 = t_inp[n + 1];
+      e_out0 = t_outp[n]; e_out1 = t_outp[n + 1];
+      j0 = t_genp[n]; j1 = t_genp[n + 1];
+      float vv[VG], pg[VG], qg[VG];
+#pragma unroll
+      for (int g = 0; g < VG; ++g) { vv[g] = 0.f; pg[g] = 0.f; qg[g] = 0.f; }
+      for (int j = j0; j < j1; ++j) {
+        const int gid = t_geni[j];
+        float x[VG];
+        IO::ld(x, s_genc + 3 * GnG + gid * G + gcol);
+#pragma unroll
+        for (int g = 0; g < VG; ++g) vv[g] += x[g];
+        IO::ld(x, s_genc + 5 * GnG + gid * G + gcol);
+#pragma unroll
+        for (int g = 0; g < VG; ++g) pg[g] += x[g];
+        IO::ld(x, s_genc + 4 * GnG + gid * G + gcol);
+#pragma unroll
+        for (int g = 0; g < VG; ++g) qg[g] += x[g];
+      }
+      float Pd[VG], Qd[VG], Gs[VG], Bs[VG], o[VG];
+      IO::ld(Pd, s_busc + 0 * NG + n * G + gcol);
+      IO::ld(Qd, s_busc + 1 * NG + n * G + gcol);
+      IO::ld(Gs, s_busc + 2 * NG + n * G + gcol);
+      IO::ld(Bs, s_busc + 3 * NG + n * G + gcol);
+      float* st = s_state + n * G + gcol;
+#pragma unroll
+      for (int g = 0; g < VG; ++g) vv[g] = (vv[g] == 0.f) ? 1.f : vv[g];
+      IO::st(st + 0 * NG, vv);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) o[g] = 0.f;
+      IO::st(st + 1 * NG, o);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) o[g] = pg[g] - Pd[g] - Gs[g] * (vv[g] * vv[g]);
+      IO::st(st + 2 * NG, o);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) o[g] = qg[g] - Qd[g] + Bs[g] * (vv[g] * vv[g]);
+      IO::st(st + 3 * NG, o);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) o[g] = 0.f;
+      for (int i = 0; i < L; ++i) IO::st(st + (4 + i) * NG, o);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) part4[0][g] = Pd[g];
+      // alias-line admittance magnitude, lines 0..N-1 (ref GNS/main.py:38,87)
+      float r[VG], x[VG], y[VG];
+      IO::ld(r, s_linef + 0 * EG + n * G + gcol);
+      IO::ld(x, s_linef + 1 * EG + n * G + gcol);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) y[g] = 1.0f / sqrtf(r[g] * r[g] + x[g] * x[g]);
+      IO::st(s_y + n * G + gcol, y);
+    }
+    for (int it = tid; it < Gn * NGQ; it += T) {
+      const int j = it / NGQ;
+      float x[VG];
+      IO::ld(x, s_genc + 2 * GnG + j * G + gcol);   // Pset
+#pragma unroll
+      for (int g = 0; g < VG; ++g) part4[1][g] += x[g];
+      IO::ld(x, s_genc + 1 * GnG + j * G + gcol);   // Pmin
+#pragma unroll
+      for (int g = 0; g < VG; ++g) part4[2][g] += x[g];
+      IO::ld(x, s_genc + 0 * GnG + j * G + gcol);   // Pmax
+#pragma unroll
+      for (int g = 0; g < VG; ++g) part4[3][g] += x[g];
+    }
+    float sPd[VG], sPset[VG], sPmin[VG], sPmax[VG];
+    block_sum_per_grid<VG>(part4[0], s_red, NGQ);
+    block_sum_per_grid<VG>(part4[1], s_red, NGQ);
+    block_sum_per_grid<VG>(part4[2], s_red, NGQ);
+    block_sum_per_grid<VG>(part4[3], s_red, NGQ);
+#pragma unroll
+    for (int g = 0; g < VG; ++g) { sPd[g] = part4[0][g]; sPset[g] = part4[1][g]; sPmin[g] = part4[2][g]; sPmax[g] = part4[3][g]; }
+    if (tid < NGQ) {  // keep per-grid sums for the backward pass as well
+      IO::st(s_gsum + 0 * G + gcol, sPd);
+    }
+
+    float loss_tot[VG], loss_last[VG];
+#pragma unroll
+    for (int g = 0; g < VG; ++g) { loss_tot[g] = 0.f; loss_last[g] = 0.f; }
+
+    for (int k = 0; k < K; ++k) {
+      // ---------------- stage this step's weights ----------------
+      {
+        const float4* src = reinterpret_cast<const float4*>(a.params + (size_t)k * W.wstep);
+        float4* dst = reinterpret_cast<float4*>(s_w);
+        for (int i = tid; i < W.wstep / 4; i += T) dst[i] = __ldg(src + i);
+      }
+      // ---------------- checkpoint: state entering step k (k >= 1) ----------------
+      if (a.need_grad && k >= 1) {
+        const int nst = (4 + L) * NG;
+        float* dstg = a.ckpt + ((size_t)batch * K + (k - 1)) * (size_t)pad4(nst);
+        for (int i = tid; i < nst; i += T) dstg[i] = s_state[i];
+      }
+      __syncthreads();
+
+      // ---------------- bus phase: phi nets, aggregation, L nets ----------------
+      if (bus_on) {
+        const int n = slot;
+        float* st = s_state + n * G + gcol;
+        const float* sm_m = st + 4 * NG;
+        const float degf = (float)(e_in1 - e_in0);
+        float st4[4][VG];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) IO::ld(st4[q], st + q * NG);
+        float dv[VG], dth[VG];
+        float A[H][VG];
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+          if (MULTI || q == 0) {
+            const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
+            float P[H][VG];
+            {
+              float b[HP];
+              load_row<HP>(b, wphi + W.phi_b1);
+#pragma unroll
+              for (int o = 0; o < H; ++o)
+#pragma unroll
+                for (int g = 0; g < VG; ++g) P[o][g] = b[o];
+            }
+#pragma unroll 4
+            for (int i = 0; i < L; ++i) {
+              float x[VG];
+              IO::ld(x, sm_m + i * NG);
+              row_axpy<H, HP, VG>(P, x, wphi + W.phi_w1m + i * HP);
+            }
+#pragma unroll
+            for (int o = 0; o < H; ++o)
+#pragma unroll
+              for (int g = 0; g < VG; ++g) A[o][g] = 0.f;
+            for (int e = e_in0; e < e_in1; ++e) {
+              const float* lf = s_linef + (int)t_ini[e] * G + gcol;
+              wphi += opaque_zero();   // keep the weight rows in shared memory (no LICM into spills)
+              float z[H][VG];
+#pragma unroll
+              for (int o = 0; o < H; ++o)
+#pragma unroll
+                for (int g = 0; g < VG; ++g) z[o][g] = P[o][g];
+#pragma unroll
+              for (int c = 0; c < 5; ++c) {
+                float x[VG];
+                IO::ld(x, lf + c * EG);
+                row_axpy<H, HP, VG>(z, x, wphi + W.phi_w1f + c * HP);
+              }
+              float z2[H][VG];
+              {
+                float b[HP];
+                load_row<HP>(b, wphi + W.phi_b2);
+#pragma unroll
+                for (int o = 0; o < H; ++o)
+#pragma unroll
+                  for (int g = 0; g < VG; ++g) { z2[o][g] = b[o]; z[o][g] = lrelu(z[o][g]); }
+              }
+#pragma unroll
+              for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(z2, z[j], wphi + W.phi_w2 + j * HP);
+#pragma unroll
+              for (int o = 0; o < H; ++o)
+#pragma unroll
+                for (int g = 0; g < VG; ++g) A[o][g] += lrelu(z2[o][g]);
+            }
+          }
+          const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
+          const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
+          float zL[H][VG];
+          {
+            float b[HP];
+            load_row<HP>(b, wln + W.ln_b1);
+#pragma unroll
+            for (int o = 0; o < H; ++o)
+#pragma unroll
+              for (int g = 0; g < VG; ++g) zL[o][g] = b[o];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) row_axpy<H, HP, VG>(zL, st4[i], wln + W.ln_w1 + i * HP);
+#pragma unroll 4
+          for (int i = 0; i < L; ++i) {
+            float x[VG];
+            IO::ld(x, sm_m + i * NG);
+            row_axpy<H, HP, VG>(zL, x, wln + W.ln_w1 + (4 + i) * HP);
+          }
+#pragma unroll 2
+          for (int i = 0; i < PO; ++i) {
+            float s[VG];
+            const float b4 = wphi[W.phi_b4 + i];
+#pragma unroll
+            for (int g = 0; g < VG; ++g) s[g] = degf * b4;
+            row_dot<H, HP, VG>(s, A, wphi + W.phi_w4 + i * HP);
+            row_axpy<H, HP, VG>(zL, s, wln + W.ln_w1 + (4 + L + i) * HP);
+          }
+          float z2[H][VG];
+          {
+            float b[HP];
+            load_row<HP>(b, wln + W.ln_b2);
+#pragma unroll
+            for (int o = 0; o < H; ++o)
+#pragma unroll
+              for (int g = 0; g < VG; ++g) { z2[o][g] = b[o]; zL[o][g] = lrelu(zL[o][g]); }
+          }
+#pragma unroll
+          for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(z2, zL[j], wln + W.ln_w2 + j * HP);
+#pragma unroll
+          for (int o = 0; o < H; ++o)
+#pragma unroll
+            for (int g = 0; g < VG; ++g) z2[o][g] = lrelu(z2[o][g]);
+          if (q < 2) {
+            float out[VG];
+            const float bo = wln[W.ln_bo_s];
+#pragma unroll
+            for (int g = 0; g < VG; ++g) out[g] = bo;
+            row_dot<H, HP, VG>(out, z2, wln + W.ln_wo);
+            if (q == 0) {
+#pragma unroll
+              for (int g = 0; g < VG; ++g) dv[g] = out[g];
+            } else {
+#pragma unroll
+              for (int g = 0; g < VG; ++g) dth[g] = out[g];
+            }
+          } else {
+#pragma unroll 2
+            for (int i = 0; i < L; ++i) {
+              float dm[VG], mi[VG];
+              const float bo = wln[W.ln_bo_m + i];
+#pragma unroll
+              for (int g = 0; g < VG; ++g) dm[g] = bo;
+              row_dot<H, HP, VG>(dm, z2, wln + W.ln_wo + i * HP);
+              IO::ld(mi, st + (4 + i) * NG);
+#pragma unroll
+              for (int g = 0; g < VG; ++g) mi[g] += dm[g];
+              IO::st(st + (4 + i) * NG, mi);
+            }
+          }
+        }
+        // state update (ref GNS/main.py:182-188); v only moves on non-generator buses
+        const bool is_gen = j1 > j0;
+#pragma unroll
+        for (int g = 0; g < VG; ++g) {
+          st4[1][g] = st4[1][g] + dth[g];
+          if (!is_gen) st4[0][g] = st4[0][g] + dv[g];
+        }
+        IO::st(st + 0 * NG, st4[0]);
+        IO::st(st + 1 * NG, st4[1]);
+      }
+      __syncthreads();
+
+      // ---------------- physics 1: angle difference of the alias lines 0..N-1 ----------------
+      if (bus_on) {
+        const int j = slot;  // used as a LINE id here
+        float tf[VG], tt[VG], d[VG], sd[VG], cd[VG];
+        IO::ld(tf, s_state + 1 * NG + (int)t_fi[j] * G + gcol);
+        IO::ld(tt, s_state + 1 * NG + (int)t_ti[j] * G + gcol);
+#pragma unroll
+        for (int g = 0; g < VG; ++g) { d[g] = tf[g] - tt[g]; fast_sincos(d[g], sd[g], cd[g]); }
+        IO::st(s_trig + 0 * NG + j * G + gcol, d);
+        IO::st(s_trig + 1 * NG + j * G + gcol, sd);
+        IO::st(s_trig + 2 * NG + j * G + gcol, cd);
+      }
+      __syncthreads();
+
+      // ---------------- physics 2: per-line flows (ref GNS/main.py:38-41,66-72,87-99) ----------------
+      float pj[VG];
+#pragma unroll
+      for (int g = 0; g < VG; ++g) pj[g] = 0.f;
+      for (int it = tid; it < E * NGQ; it += T) {
+        const int e = it / NGQ;
+        const int fi = t_fi[e], ti = t_ti[e], fa = t_fa[e], ta = t_ta[e];
+        float vf[VG], vt[VG], thf[VG], tht[VG];
+        IO::ld(vf, s_state + 0 * NG + fi * G + gcol);
+        IO::ld(vt, s_state + 0 * NG + ti * G + gcol);
+        IO::ld(thf, s_state + 1 * NG + fi * G + gcol);
+        IO::ld(tht, s_state + 1 * NG + ti * G + gcol);
+        float Yf[VG], tauf[VG], shf[VG], bf[VG], Df[VG], sDf[VG], cDf[VG];
+        IO::ld(Yf, s_y + fa * G + gcol);
+        IO::ld(bf, s_linef + 2 * EG + fa * G + gcol);
+        IO::ld(tauf, s_linef + 3 * EG + fa * G + gcol);
+        IO::ld(shf, s_linef + 4 * EG + fa * G + gcol);
+        IO::ld(Df, s_trig + 0 * NG + fa * G + gcol);
+        IO::ld(sDf, s_trig + 1 * NG + fa * G + gcol);
+        IO::ld(cDf, s_trig + 2 * NG + fa * G + gcol);
+        float Yt[VG], taut[VG], sht[VG], bt[VG], Dt[VG], sDt[VG];
+        IO::ld(Yt, s_y + ta * G + gcol);
+        IO::ld(bt, s_linef + 2 * EG + ta * G + gcol);
+        IO::ld(taut, s_linef + 3 * EG + ta * G + gcol);
+        IO::ld(sht, s_linef + 4 * EG + ta * G + gcol);
+        IO::ld(Dt, s_trig + 0 * NG + ta * G + gcol);
+        IO::ld(sDt, s_trig + 1 * NG + ta * G + gcol);
+        float pf[VG], qf[VG], pt[VG], qt[VG];
+#pragma unroll
+        for (int g = 0; g < VG; ++g) {
+          const float dt = -Dt[g], sdt = -sDt[g];       // delta_ji = -delta_ij, re-read through the alias
+          const float a1 = thf[g] - tht[g] - Df[g] - shf[g];
+          const float a2 = tht[g] - thf[g] - Df[g] + shf[g];
+          const float a3 = tht[g] - thf[g] - dt - sht[g];
+          float s1, c1, s2, c2, s3, c3;
+          fast_sincos(a1, s1, c1);
+          fast_sincos(a2, s2, c2);
+          fast_sincos(a3, s3, c3);
+          (void)c2;
+          const float t1 = vf[g] * vt[g] * Yf[g] / tauf[g];
+          const float vft = vf[g] / tauf[g];
+          const float msg = fabsf(t1 * (s1 + s2) + (vf[g] / (tauf[g] * tauf[g])) * Yf[g] * sDf[g] +
+                                  (vt[g] * vt[g]) * Yf[g] * sDf[g]);
+          pj[g] += msg;
+          pf[g] = t1 * s1 + (vft * vft) * Yf[g] * sDf[g];
+          qf[g] = -t1 * c1 + (vft * vft) * (Yf[g] * cDf[g] - bf[g] / 2.f);
+          const float u1 = vt[g] * vf[g] * Yt[g] / taut[g];
+          pt[g] = u1 * s3 + (vt[g] * vt[g]) * Yt[g] * sdt;
+          qt[g] = -u1 * c3 + (vt[g] * vt[g]) * (Yt[g] * sdt - bt[g] / 2.f);
+        }
+        IO::st(s_flow + 0 * EG + e * G + gcol, pf);
+        IO::st(s_flow + 1 * EG + e * G + gcol, qf);
+        IO::st(s_flow + 2 * EG + e * G + gcol, pt);
+        IO::st(s_flow + 3 * EG + e * G + gcol, qt);
+      }
+      float v_own[VG], Gs[VG], Bs[VG];
+      if (bus_on) {
+        IO::ld(v_own, s_state + 0 * NG + slot * G + gcol);
+        IO::ld(Gs, s_busc + 2 * NG + slot * G + gcol);
+        IO::ld(Bs, s_busc + 3 * NG + slot * G + gcol);
+#pragma unroll
+        for (int g = 0; g < VG; ++g) pj[g] += (v_own[g] * v_own[g]) * Gs[g];
+      }
+      block_sum_per_grid<VG>(pj, s_red, NGQ);   // also orders the s_flow writes before the gathers
+
+      // ---------------- physics 3: slack redistribution + per-bus mismatch ----------------
+      float lam[VG];
+      bool lo_arm[VG];
+#pragma unroll
+      for (int g = 0; g < VG; ++g) {
+        const float pglob = sPd[g] + pj[g];
+        pj[g] = pglob;
+        const float l1 = (pglob - sPmin[g]) / (2.f * (sPset[g] - sPmin[g]));
+        const float l2 = (pglob - 2.f * sPset[g] + sPmax[g]) / (2.f * (sPmax[g] - sPset[g]));
+        lam[g] = (pglob < sPset[g]) ? l1 : l2;
+        lo_arm[g] = lam[g] < 0.5f;
+      }
+      if (a.need_grad && tid < NGQ) IO::st(a.pglob + ((size_t)batch * K + k) * G + gcol, pj);
+      if (bus_on) {
+        const int n = slot;
+        float pgs[VG];
+#pragma unroll
+        for (int g = 0; g < VG; ++g) pgs[g] = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          const int gid = t_geni[j];
+          float Pmax[VG], Pmin[VG], Pset[VG];
+          IO::ld(Pmax, s_genc + 0 * GnG + gid * G + gcol);
+          IO::ld(Pmin, s_genc + 1 * GnG + gid * G + gcol);
+          IO::ld(Pset, s_genc + 2 * GnG + gid * G + gcol);
+#pragma unroll
+          for (int g = 0; g < VG; ++g)
+            pgs[g] += lo_arm[g] ? (Pmin[g] + 2.f * (Pset[g] - Pmin[g]) * lam[g])
+                                : (2.f * Pset[g] - Pmax[g] + 2.f * (Pmax[g] - Pset[g]) * lam[g]);
+        }
+        float spf[VG], sqf[VG], spt[VG], sqt[VG];
+#pragma unroll
+        for (int g = 0; g < VG; ++g) { spf[g] = 0.f; sqf[g] = 0.f; spt[g] = 0.f; sqt[g] = 0.f; }
+        for (int e = e_in0; e < e_in1; ++e) {
+          const int line = t_ini[e];
+          float x[VG];
+          IO::ld(x, s_flow + 0 * EG + line * G + gcol);
+#pragma unroll
+          for (int g = 0; g < VG; ++g) spf[g] += x[g];
+          IO::ld(x, s_flow + 1 * EG + line * G + gcol);
+#pragma unroll
+          for (int g = 0; g < VG; ++g) sqf[g] += x[g];
+        }
+        for (int e = e_out0; e < e_out1; ++e) {
+          const int line = t_outi[e];
+          float x[VG];
+          IO::ld(x, s_flow + 2 * EG + line * G + gcol);
+#pragma unroll
+          for (int g = 0; g < VG; ++g) spt[g] += x[g];
+          IO::ld(x, s_flow + 3 * EG + line * G + gcol);
+#pragma unroll
+          for (int g = 0; g < VG; ++g) sqt[g] += x[g];
+        }
+        float Pd[VG], Qd[VG], dP[VG], dQ[VG];
+        IO::ld(Pd, s_busc + 0 * NG + n * G + gcol);
+        IO::ld(Qd, s_busc + 1 * NG + n * G + gcol);
+        const float wk = a.wk[k];
+#pragma unroll
+        for (int g = 0; g < VG; ++g) {
+          const float v2 = v_own[g] * v_own[g];
+          const float qg = (Qd[g] - Bs[g] * v2) - sqf[g] - sqt[g];
+          dP[g] = pgs[g] - Pd[g] - Gs[g] * v2 + spf[g] + spt[g];
+          dQ[g] = qg - Qd[g] + Bs[g] * v2 + sqf[g] + sqt[g];
+          const float sq = dP[g] * dP[g] + dQ[g] * dQ[g];
+          loss_tot[g] = fmaf(wk, sq, loss_tot[g]);
+          loss_last[g] = sq;
+        }
+        IO::st(s_state + 2 * NG + n * G + gcol, dP);
+        IO::st(s_state + 3 * NG + n * G + gcol, dQ);
+      }
+      __syncthreads();
+    }  // k
+
+    // ---------------- outputs ----------------
+    if (a.need_grad) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
+      const int nst = (4 + L) * NG;
+      float* dstg = a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)pad4(nst);
+      for (int i = tid; i < nst; i += T) dstg[i] = s_state[i];
+    }
+    block_sum_per_grid<VG>(loss_tot, s_red, NGQ);
+    block_sum_per_grid<VG>(loss_last, s_red, NGQ);
+    if (tid < NGQ) {
+#pragma unroll
+      for (int g = 0; g < VG; ++g) {
+        const long long gg = g0 + gcol + g;
+        if (gg < a.S) {
+          a.total[gg] = loss_tot[g] / (float)N;
+          a.last[gg] = loss_last[g] / (float)N;
+        }
+      }
+    }
+    if (bus_on) {
+      const int ext = t_ext[slot];
+      float vv[VG], th[VG];
+      IO::ld(vv, s_state + 0 * NG + slot * G + gcol);
+      IO::ld(th, s_state + 1 * NG + slot * G + gcol);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) {
+        const long long gg = g0 + gcol + g;
+        if (gg < a.S) {
+          a.v[gg * N + ext] = (vv[g] < 0.f) ? 0.f : vv[g];   // ref GNS/main.py:201
+          a.theta[gg * N + ext] = th[g];
+        }
+      }
+    }
+    __syncthreads();
+  }  // batch
+}
+
+}  // namespace gns

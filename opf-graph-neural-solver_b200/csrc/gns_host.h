@@ -1,0 +1,69 @@
+// gns_host.h — host-side plan object and launch geometry (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "gns_common.cuh"
+
+struct gns_plan {
+  int device = 0;
+  int N = 0, E = 0, Gn = 0;
+  int num_sms = 0;
+  int smem_optin = 0;
+  // host copies (int32) for export and tests
+  std::vector<int32_t> f_bus, t_bus, gen_bus;
+  std::vector<int32_t> in_rowptr, in_lines, out_rowptr, out_lines, gen_rowptr, gen_ids;
+  std::vector<int32_t> bus_order, bus_rank;
+  // device index block (uint16) + float copies of the expected index columns
+  gns::TopoOffsets to{};
+  uint16_t* d_topo = nullptr;
+  float* d_expect = nullptr;        // [2E + Gn]: f_bus+1, t_bus+1, gen_bus+1 as float (topology check)
+  int* d_flag = nullptr;
+  // canonical(state_dict order) -> packed index maps, cached per (K,L,H,multi)
+  struct PackMap { int32_t* d_map = nullptr; int64_t n_canon = 0; int64_t n_packed = 0; };
+  std::map<std::tuple<int, int, int, int>, PackMap> pack_maps;
+};
+
+namespace gns {
+
+struct Geometry {
+  int VG = 1, NGQ = 1, G = 1, T = 32;
+  int tmax = 384;           // launch-bounds variant
+  int nbatch = 0, ctas = 0, num_sms = 0;
+  size_t smem_bytes = 0;
+  SmemPlan sm{};
+};
+
+struct ModelDims { int K, L, H, multi; };
+
+void set_error(const std::string& msg);
+
+// workspace carving (all offsets in bytes, 256-byte aligned)
+struct Workspace {
+  size_t packed_params = 0;   // [K][wstep] floats
+  size_t ckpt = 0;            // [nbatch][K][pad4((4+L) N G)] floats   (need_grad)
+  size_t pglob = 0;           // [nbatch][K][G] floats                 (need_grad)
+  size_t gpartial = 0;        // [ctas][K][wstep] floats               (need_grad): per-CTA gradient partial sums
+  size_t packed_grad = 0;     // [K][wstep] floats                     (need_grad)
+  size_t total = 0;
+};
+
+bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, bool backward, Geometry* out);
+Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S, bool need_grad,
+                         const Geometry& fwd, const Geometry& bwd);
+
+// canonical <-> packed parameter maps
+int64_t canonical_param_count(const ModelDims& md);
+std::vector<int32_t> build_pack_map(const ModelDims& md);   // canonical index -> packed index
+const gns_plan::PackMap* get_pack_map(gns_plan* plan, const ModelDims& md);
+
+// kernel launchers (defined in the per-dimension translation units)
+typedef cudaError_t (*FwdLauncher)(const FwdArgs& a, const Geometry& g, cudaStream_t st);
+FwdLauncher find_forward(int L, int H, int multi, int VG, int tmax);
+
+}  // namespace gns

@@ -1,0 +1,34 @@
+// gns_inst.cuh — explicit instantiation of the kernels for one latent_dim (GNS_INST_L),
+// hidden_dim 10.  Included by gns_inst_l*.cu so the variants compile in parallel.
+#pragma once
+#include "gns_forward.cuh"
+#include "gns_host.h"
+
+namespace gns {
+
+template <int L, int H, bool MULTI, int VG, int TMAX>
+static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
+  auto kern = gns_forward_kernel<L, H, MULTI, VG, TMAX>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, g.T, g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  const int ctas = std::min(g.nbatch, occ * g.num_sms);
+  kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int L, int H>
+static FwdLauncher pick_forward(int multi, int VG, int tmax) {
+  if (tmax == 384) {
+    if (VG == 2) return multi ? launch_forward<L, H, true, 2, 384> : launch_forward<L, H, false, 2, 384>;
+    if (VG == 1) return multi ? launch_forward<L, H, true, 1, 384> : launch_forward<L, H, false, 1, 384>;
+  } else if (tmax == 1024 && VG == 1) {
+    return multi ? launch_forward<L, H, true, 1, 1024> : launch_forward<L, H, false, 1, 1024>;
+  }
+  return nullptr;
+}
+
+}  // namespace gns

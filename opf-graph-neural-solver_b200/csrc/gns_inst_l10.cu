@@ -1,0 +1,6 @@
+// kernels for latent_dim = 10, hidden_dim = 10
+#include <algorithm>
+#include "gns_inst.cuh"
+namespace gns {
+FwdLauncher find_forward_l10(int multi, int VG, int tmax) { return pick_forward<10, 10>(multi, VG, tmax); }
+}  // namespace gns

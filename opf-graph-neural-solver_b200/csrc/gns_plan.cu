@@ -1,0 +1,332 @@
+// gns_plan.cu — topology plan: CSR construction, internal bus order, index block upload,
+// launch geometry, workspace carving, canonical<->packed parameter maps.
+//
+// Replaces the index tensors the reference rebuilds inside every forward call
+// (ref GNS/main.py:35-36, 85-86, 144, 153, 184-185) by a one-time plan.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "gns_host.h"
+#include "../../include/gns_b200.h"
+
+namespace gns {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+#define GNS_CUDA_OK(expr)                                                            \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+      return -2;                                                                     \
+    }                                                                                \
+  } while (0)
+
+// stable counting sort of line ids by key
+static void csr_by(const std::vector<int32_t>& key, int nb, std::vector<int32_t>& rowptr,
+                   std::vector<int32_t>& ids) {
+  rowptr.assign(nb + 1, 0);
+  for (int32_t k : key) rowptr[k + 1]++;
+  for (int i = 0; i < nb; ++i) rowptr[i + 1] += rowptr[i];
+  ids.assign(key.size(), 0);
+  std::vector<int32_t> cur(rowptr.begin(), rowptr.end() - 1);
+  for (int32_t e = 0; e < (int32_t)key.size(); ++e) ids[cur[key[e]]++] = e;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : dflt;
+}
+
+static SmemPlan plan_smem(int N, int E, int Gn, int G, int L, int wstep, int nwarps, int topo_u16,
+                          int extra_floats) {
+  SmemPlan s{};
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += pad4(n); return r; };
+  s.state = take((4 + L) * N * G);
+  s.busc = take(4 * N * G);
+  s.genc = take(6 * Gn * G);
+  s.linef = take(5 * E * G);
+  s.yline = take(N * G);
+  s.trig = take(3 * N * G);
+  s.flows = take(4 * E * G);
+  s.gsum = take(4 * G);
+  s.red = take(nwarps * G);
+  s.weights = take(wstep);
+  s.topo = take((topo_u16 + 1) / 2);
+  s.extra = o;
+  o += pad4(extra_floats);
+  s.total_floats = o;
+  return s;
+}
+
+// extra shared memory of the backward kernel, in floats (see gns_backward.cuh)
+int backward_extra_floats(int N, int E, int G, int L, int H, int T);
+
+bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, bool backward, Geometry* out) {
+  const int N = plan->N, E = plan->E, Gn = plan->Gn;
+  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
+  const int limit = plan->smem_optin;
+  Geometry best{};
+  bool found = false;
+  const int force_vg = env_int(backward ? "GNS_BWD_VG" : "GNS_FWD_VG", 0);
+  const int force_ngq = env_int(backward ? "GNS_BWD_NGQ" : "GNS_FWD_NGQ", 0);
+  const int target_threads = env_int("GNS_TARGET_THREADS", 320);
+  for (int VG : {2, 1}) {
+    if (force_vg && VG != force_vg) continue;
+    // small batches: one grid per thread so that the batch spreads over more SMs
+    if (!force_vg && VG == 2 && (S + 1) / 2 < plan->num_sms) continue;
+    for (int NGQ = 32; NGQ >= 1; NGQ >>= 1) {
+      if (force_ngq && NGQ != force_ngq) continue;
+      const int T = ((N * NGQ + 31) / 32) * 32;
+      if (T > 1024) continue;
+      const int G = VG * NGQ;
+      const long long nb = (S + G - 1) / G;
+      if (!force_ngq && NGQ > 1 && (T > std::max(target_threads, 32) || nb < 2LL * plan->num_sms)) continue;
+      Geometry g{};
+      g.VG = VG; g.NGQ = NGQ; g.G = G; g.T = T;
+      g.tmax = (T <= 384) ? 384 : 1024;
+      if (g.tmax == 1024 && VG != 1) continue;   // the wide-CTA variant exists for VG=1 only
+      const int extra = backward ? backward_extra_floats(N, E, G, md.L, md.H, T) : 0;
+      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra);
+      const size_t bytes = (size_t)sm.total_floats * 4;
+      if ((int)bytes > limit) continue;
+      g.smem_bytes = bytes; g.sm = sm;
+      g.nbatch = (int)nb; g.num_sms = plan->num_sms;
+      best = g; found = true;
+      break;
+    }
+    if (found) break;
+  }
+  if (!found) {
+    set_error("no launch geometry fits: n_bus=" + std::to_string(N) + " n_line=" + std::to_string(E) +
+              " latent_dim=" + std::to_string(md.L) + " (shared memory limit " + std::to_string(limit) + " B)");
+    return false;
+  }
+  *out = best;
+  return true;
+}
+
+int64_t canonical_param_count(const ModelDims& md) {
+  const int64_t L = md.L, H = md.H;
+  const int64_t phi_out = md.multi ? L : 1;
+  const int64_t phi = (5 + L) * H + H + H * H + H + phi_out * H + phi_out;
+  const int64_t ls = (4 + 2 * L) * H + H + H * H + H + H + 1;
+  const int64_t lm = (4 + 2 * L) * H + H + H * H + H + L * H + L;
+  return (int64_t)md.K * ((md.multi ? 3 : 1) * phi + 2 * ls + lm);
+}
+
+// canonical (state_dict order) index -> packed [K][wstep] index
+std::vector<int32_t> build_pack_map(const ModelDims& md) {
+  const int L = md.L, H = md.H, K = md.K;
+  const bool multi = md.multi != 0;
+  const WLayout W = make_wlayout(L, H, multi);
+  std::vector<int32_t> map;
+  map.reserve((size_t)canonical_param_count(md));
+  // canonical net order: phi_v, phi_theta, phi_m | phi ; L_theta, L_v, L_m
+  struct Net { bool is_phi; int pair; };   // pair: 0 = v, 1 = theta, 2 = m
+  std::vector<Net> nets;
+  if (multi) { nets.push_back({true, 0}); nets.push_back({true, 1}); nets.push_back({true, 2}); }
+  else nets.push_back({true, 0});
+  nets.push_back({false, 1}); nets.push_back({false, 0}); nets.push_back({false, 2});
+  for (const Net& net : nets) {
+    for (int k = 0; k < K; ++k) {
+      const int base = k * W.wstep + (net.is_phi ? W.off_phi[net.pair] : W.off_ln[net.pair]);
+      if (net.is_phi) {
+        const int din = 5 + L, dout = multi ? L : 1;
+        for (int o = 0; o < H; ++o)            // linear1.weight [H][din], inputs = [m (L), features (5)]
+          for (int i = 0; i < din; ++i)
+            map.push_back(base + (i < L ? W.phi_w1m + i * W.HP + o : W.phi_w1f + (i - L) * W.HP + o));
+        for (int o = 0; o < H; ++o) map.push_back(base + W.phi_b1 + o);
+        for (int o = 0; o < H; ++o)            // linear2.weight [H][H]
+          for (int j = 0; j < H; ++j) map.push_back(base + W.phi_w2 + j * W.HP + o);
+        for (int o = 0; o < H; ++o) map.push_back(base + W.phi_b2 + o);
+        for (int i = 0; i < dout; ++i)         // linear4.weight [dout][H]
+          for (int j = 0; j < H; ++j) map.push_back(base + W.phi_w4 + i * W.HP + j);
+        for (int i = 0; i < dout; ++i) map.push_back(base + W.phi_b4 + i);
+      } else {
+        const int din = 4 + 2 * L, dout = (net.pair == 2) ? L : 1;
+        for (int o = 0; o < H; ++o)
+          for (int i = 0; i < din; ++i) map.push_back(base + W.ln_w1 + i * W.HP + o);
+        for (int o = 0; o < H; ++o) map.push_back(base + W.ln_b1 + o);
+        for (int o = 0; o < H; ++o)
+          for (int j = 0; j < H; ++j) map.push_back(base + W.ln_w2 + j * W.HP + o);
+        for (int o = 0; o < H; ++o) map.push_back(base + W.ln_b2 + o);
+        for (int i = 0; i < dout; ++i)
+          for (int j = 0; j < H; ++j) map.push_back(base + W.ln_wo + i * W.HP + j);
+        const int bo = (net.pair == 2) ? W.ln_bo_m : W.ln_bo_s;
+        for (int i = 0; i < dout; ++i) map.push_back(base + bo + i);
+      }
+    }
+  }
+  return map;
+}
+
+const gns_plan::PackMap* get_pack_map(gns_plan* plan, const ModelDims& md) {
+  auto key = std::make_tuple(md.K, md.L, md.H, md.multi);
+  auto it = plan->pack_maps.find(key);
+  if (it != plan->pack_maps.end()) return &it->second;
+  std::vector<int32_t> map = build_pack_map(md);
+  gns_plan::PackMap pm;
+  pm.n_canon = (int64_t)map.size();
+  pm.n_packed = (int64_t)md.K * make_wlayout(md.L, md.H, md.multi != 0).wstep;
+  if (cudaMalloc(&pm.d_map, map.size() * sizeof(int32_t)) != cudaSuccess) { set_error("cudaMalloc(pack map) failed"); return nullptr; }
+  if (cudaMemcpy(pm.d_map, map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("cudaMemcpy(pack map) failed"); return nullptr;
+  }
+  auto res = plan->pack_maps.emplace(key, pm);
+  return &res.first->second;
+}
+
+Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S, bool need_grad,
+                         const Geometry& fwd, const Geometry& bwd) {
+  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  Workspace w{};
+  size_t o = 0;
+  w.packed_params = o; o = align(o + (size_t)md.K * W.wstep * 4);
+  if (need_grad) {
+    const size_t nst = (size_t)pad4((4 + md.L) * plan->N * fwd.G);
+    w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
+    w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
+    w.gpartial = o; o = align(o + (size_t)bwd.ctas * md.K * W.wstep * 4);
+    w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
+  }
+  w.total = o;
+  return w;
+}
+
+}  // namespace gns
+
+using namespace gns;
+
+extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* f_bus, const int32_t* t_bus,
+                               const int32_t* gen_bus, int device, gns_plan** out_plan) {
+  if (!out_plan) { set_error("out_plan is null"); return -1; }
+  *out_plan = nullptr;
+  if (n_bus <= 0 || n_line <= 0 || n_gen < 0 || !f_bus || !t_bus || (n_gen > 0 && !gen_bus)) {
+    set_error("gns_plan_create: empty topology"); return -1;
+  }
+  if (n_bus > 65535 || n_line > 65535 || n_gen > 65535) { set_error("gns_plan_create: sizes must be < 65536"); return -1; }
+  if (n_bus > n_line) {
+    set_error("gns_plan_create: n_bus > n_line; the reference indexes per-line vectors with bus numbers "
+              "(ref GNS/main.py:41) and would raise IndexError");
+    return -1;
+  }
+  for (int e = 0; e < n_line; ++e)
+    if (f_bus[e] < 0 || f_bus[e] >= n_bus || t_bus[e] < 0 || t_bus[e] >= n_bus) {
+      set_error("gns_plan_create: line " + std::to_string(e) + " has a bus index outside [0, n_bus) "
+                "(bus ids must be contiguous 1..n_bus like the reference requires, ref GNS/main.py:153)");
+      return -1;
+    }
+  for (int j = 0; j < n_gen; ++j)
+    if (gen_bus[j] < 0 || gen_bus[j] >= n_bus) { set_error("gns_plan_create: generator bus out of range"); return -1; }
+
+  gns_plan* p = new gns_plan();
+  p->device = device; p->N = n_bus; p->E = n_line; p->Gn = n_gen;
+  p->f_bus.assign(f_bus, f_bus + n_line);
+  p->t_bus.assign(t_bus, t_bus + n_line);
+  p->gen_bus.assign(gen_bus, gen_bus + n_gen);
+
+  // CSR in EXTERNAL bus numbering (exported, bit-exact against numpy argsort(stable)+bincount)
+  csr_by(p->t_bus, n_bus, p->in_rowptr, p->in_lines);
+  csr_by(p->f_bus, n_bus, p->out_rowptr, p->out_lines);
+  csr_by(p->gen_bus, n_bus, p->gen_rowptr, p->gen_ids);
+  // internal order: in-degree descending, stable
+  p->bus_order.resize(n_bus);
+  std::iota(p->bus_order.begin(), p->bus_order.end(), 0);
+  std::stable_sort(p->bus_order.begin(), p->bus_order.end(), [&](int32_t a, int32_t b) {
+    return (p->in_rowptr[a + 1] - p->in_rowptr[a]) > (p->in_rowptr[b + 1] - p->in_rowptr[b]);
+  });
+  p->bus_rank.resize(n_bus);
+  for (int s = 0; s < n_bus; ++s) p->bus_rank[p->bus_order[s]] = s;
+
+  // device index block in INTERNAL slot numbering
+  p->to = make_topo_offsets(n_bus, n_line, n_gen);
+  std::vector<uint16_t> blk(p->to.total, 0);
+  for (int e = 0; e < n_line; ++e) {
+    blk[p->to.fi + e] = (uint16_t)p->bus_rank[f_bus[e]];
+    blk[p->to.ti + e] = (uint16_t)p->bus_rank[t_bus[e]];
+    blk[p->to.fa + e] = (uint16_t)f_bus[e];
+    blk[p->to.ta + e] = (uint16_t)t_bus[e];
+  }
+  {
+    int oi = 0, oo = 0, og = 0;
+    for (int s = 0; s < n_bus; ++s) {
+      const int b = p->bus_order[s];
+      blk[p->to.in_ptr + s] = (uint16_t)oi;
+      for (int q = p->in_rowptr[b]; q < p->in_rowptr[b + 1]; ++q) blk[p->to.in_ids + oi++] = (uint16_t)p->in_lines[q];
+      blk[p->to.out_ptr + s] = (uint16_t)oo;
+      for (int q = p->out_rowptr[b]; q < p->out_rowptr[b + 1]; ++q) blk[p->to.out_ids + oo++] = (uint16_t)p->out_lines[q];
+      blk[p->to.gen_ptr + s] = (uint16_t)og;
+      for (int q = p->gen_rowptr[b]; q < p->gen_rowptr[b + 1]; ++q) blk[p->to.gen_ids + og++] = (uint16_t)p->gen_ids[q];
+      blk[p->to.ext_of + s] = (uint16_t)b;
+      blk[p->to.rank_of + b] = (uint16_t)s;
+    }
+    blk[p->to.in_ptr + n_bus] = (uint16_t)oi;
+    blk[p->to.out_ptr + n_bus] = (uint16_t)oo;
+    blk[p->to.gen_ptr + n_bus] = (uint16_t)og;
+  }
+  std::vector<float> expect(2 * n_line + n_gen);
+  for (int e = 0; e < n_line; ++e) { expect[e] = (float)(f_bus[e] + 1); expect[n_line + e] = (float)(t_bus[e] + 1); }
+  for (int j = 0; j < n_gen; ++j) expect[2 * n_line + j] = (float)(gen_bus[j] + 1);
+
+  auto fail = [&](const char* what) { set_error(what); gns_plan_destroy(p); return -2; };
+  if (device < 0) {   // host-only plan: index arrays for export, nothing uploaded (used by CPU tests)
+    *out_plan = p;
+    return 0;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
+  p->num_sms = prop.multiProcessorCount;
+  p->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cudaMalloc(&p->d_topo, blk.size() * sizeof(uint16_t)) != cudaSuccess) return fail("cudaMalloc(topo) failed");
+  if (cudaMemcpy(p->d_topo, blk.data(), blk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail("cudaMemcpy(topo) failed");
+  if (cudaMalloc(&p->d_expect, expect.size() * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(expect) failed");
+  if (cudaMemcpy(p->d_expect, expect.data(), expect.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail("cudaMemcpy(expect) failed");
+  if (cudaMalloc(&p->d_flag, sizeof(int)) != cudaSuccess) return fail("cudaMalloc(flag) failed");
+  *out_plan = p;
+  return 0;
+}
+
+extern "C" void gns_plan_destroy(gns_plan* p) {
+  if (!p) return;
+  if (p->device < 0) { delete p; return; }
+  cudaSetDevice(p->device);
+  if (p->d_topo) cudaFree(p->d_topo);
+  if (p->d_expect) cudaFree(p->d_expect);
+  if (p->d_flag) cudaFree(p->d_flag);
+  for (auto& kv : p->pack_maps) if (kv.second.d_map) cudaFree(kv.second.d_map);
+  delete p;
+}
+
+extern "C" int gns_plan_export(const gns_plan* p, const char* name, int32_t* out, int capacity) {
+  if (!p || !name) return -1;
+  const std::vector<int32_t>* v = nullptr;
+  const std::string s(name);
+  if (s == "in_rowptr") v = &p->in_rowptr;
+  else if (s == "in_lines") v = &p->in_lines;
+  else if (s == "out_rowptr") v = &p->out_rowptr;
+  else if (s == "out_lines") v = &p->out_lines;
+  else if (s == "gen_rowptr") v = &p->gen_rowptr;
+  else if (s == "gen_ids") v = &p->gen_ids;
+  else if (s == "bus_order") v = &p->bus_order;
+  else if (s == "bus_rank") v = &p->bus_rank;
+  else { set_error("gns_plan_export: unknown array '" + s + "'"); return -1; }
+  if (out) {
+    if (capacity < (int)v->size()) { set_error("gns_plan_export: capacity too small"); return -1; }
+    std::memcpy(out, v->data(), v->size() * sizeof(int32_t));
+  }
+  return (int)v->size();
+}
+
+extern "C" int64_t gns_param_count(int K, int L, int H, int multi) {
+  return canonical_param_count(ModelDims{K, L, H, multi});
+}

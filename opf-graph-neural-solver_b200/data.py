@@ -1,0 +1,159 @@
+"""Grid tables -> packed tensors, and the synthetic load-perturbed samples used for
+measurement (host-side PyTorch / numpy; not on the GPU hot path).
+
+* ``pack_grids``   restates ``prepare_grid``  (ref GNS/utils.py:17-41), batched and bit-exact
+* ``augment``      restates the perturbation recipe of ref GNS/augment_grids.py:25-54 with a
+                   seeded ``numpy.random.default_rng`` (the reference uses unseeded ``np.random``)
+* ``case14``       the IEEE 14-bus table (standard public test case; same numbers as
+                   ``data/case14/augmented_case14_0.pkl`` of the reference)
+* ``synthetic_case`` an IEEE-*sized* random topology for 30 / 118 / 300 buses: the real
+                   tables ship with pypower, which is not available offline.
+                   Results obtained on these are labelled "IEEE-sized synthetic topology".
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+# n_bus -> (n_line, n_gen), ref GNS/utils.py:45-56
+IEEE_SIZES = {14: (20, 5), 30: (41, 6), 118: (186, 54), 300: (411, 69)}
+
+# pypower column numbers (caseformat): bus 13 cols, branch 13 cols, gen 21 cols
+_BUS_I, _BUS_TYPE, _PD, _QD, _GS, _BS = 0, 1, 2, 3, 4, 5
+_F, _T, _R, _X, _B, _TAP, _SHIFT = 0, 1, 2, 3, 4, 8, 9
+_GBUS, _PG, _QG, _VG, _PMAX, _PMIN = 0, 1, 2, 5, 8, 9
+
+
+def _tables(bus6, br7, gen6, base_mva=100.0):
+    bus = np.zeros((len(bus6), 13)); branch = np.zeros((len(br7), 13)); gen = np.zeros((len(gen6), 21))
+    bus[:, :6] = bus6
+    branch[:, [_F, _T, _R, _X, _B, _TAP, _SHIFT]] = br7
+    gen[:, [_GBUS, _PMAX, _PMIN, _PG, _VG, _QG]] = gen6
+    return {"baseMVA": float(base_mva), "bus": bus, "branch": branch, "gen": gen}
+
+
+def case14():
+    """IEEE 14-bus test case (bus: id,type,Pd,Qd,Gs,Bs; branch: f,t,r,x,b,ratio,angle;
+    gen: bus,Pmax,Pmin,Pg,Vg,Qg)."""
+    bus = [[1, 3, 0, 0, 0, 0], [2, 2, 21.7, 12.7, 0, 0], [3, 2, 94.2, 19, 0, 0], [4, 1, 47.8, -3.9, 0, 0],
+           [5, 1, 7.6, 1.6, 0, 0], [6, 2, 11.2, 7.5, 0, 0], [7, 1, 0, 0, 0, 0], [8, 2, 0, 0, 0, 0],
+           [9, 1, 29.5, 16.6, 0, 19], [10, 1, 9, 5.8, 0, 0], [11, 1, 3.5, 1.8, 0, 0], [12, 1, 6.1, 1.6, 0, 0],
+           [13, 1, 13.5, 5.8, 0, 0], [14, 1, 14.9, 5, 0, 0]]
+    br = [[1, 2, 0.01938, 0.05917, 0.0528, 0, 0], [1, 5, 0.05403, 0.22304, 0.0492, 0, 0],
+          [2, 3, 0.04699, 0.19797, 0.0438, 0, 0], [2, 4, 0.05811, 0.17632, 0.034, 0, 0],
+          [2, 5, 0.05695, 0.17388, 0.0346, 0, 0], [3, 4, 0.06701, 0.17103, 0.0128, 0, 0],
+          [4, 5, 0.01335, 0.04211, 0, 0, 0], [4, 7, 0, 0.20912, 0, 0.978, 0], [4, 9, 0, 0.55618, 0, 0.969, 0],
+          [5, 6, 0, 0.25202, 0, 0.932, 0], [6, 11, 0.09498, 0.1989, 0, 0, 0], [6, 12, 0.12291, 0.25581, 0, 0, 0],
+          [6, 13, 0.06615, 0.13027, 0, 0, 0], [7, 8, 0, 0.17615, 0, 0, 0], [7, 9, 0, 0.11001, 0, 0, 0],
+          [9, 10, 0.03181, 0.0845, 0, 0, 0], [9, 14, 0.12711, 0.27038, 0, 0, 0], [10, 11, 0.08205, 0.19207, 0, 0, 0],
+          [12, 13, 0.22092, 0.19988, 0, 0, 0], [13, 14, 0.17093, 0.34802, 0, 0, 0]]
+    gen = [[1, 332.4, 0, 232.4, 1.06, -16.9], [2, 140, 0, 40, 1.045, 42.4], [3, 100, 0, 0, 1.01, 23.4],
+           [6, 100, 0, 0, 1.07, 12.2], [8, 100, 0, 0, 1.09, 17.4]]
+    return _tables(np.array(bus, float), np.array(br, float), np.array(gen, float))
+
+
+def synthetic_case(n_bus: int, n_line: int | None = None, n_gen: int | None = None, seed: int = 0):
+    """IEEE-sized synthetic topology: seeded random spanning tree plus chords (parallel
+    lines allowed, no self loops), contiguous bus ids 1..n_bus, generators on distinct
+    buses, base values drawn from case14-like ranges."""
+    if n_line is None or n_gen is None:
+        n_line, n_gen = IEEE_SIZES[n_bus]
+    if n_line < n_bus:
+        raise ValueError("need n_line >= n_bus (the reference indexes line vectors by bus number)")
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(n_bus)
+    f, t = [], []
+    for i in range(1, n_bus):                       # spanning tree
+        a, b = order[i], order[rng.integers(0, i)]
+        f.append(min(a, b)); t.append(max(a, b))
+    while len(f) < n_line:                          # chords
+        a, b = rng.integers(0, n_bus, size=2)
+        if a != b:
+            f.append(min(a, b)); t.append(max(a, b))
+    idx = np.lexsort((t, f))                        # sorted by (f, t) like the IEEE tables
+    f, t = np.array(f)[idx] + 1, np.array(t)[idx] + 1
+    br = np.zeros((n_line, 7))
+    br[:, 0], br[:, 1] = f, t
+    br[:, 2] = rng.uniform(0.0, 0.24, n_line)
+    br[:, 3] = rng.uniform(0.04, 0.61, n_line)
+    br[:, 4] = rng.uniform(0.0, 0.06, n_line)
+    gen_bus = np.sort(rng.choice(n_bus, size=n_gen, replace=False)) + 1
+    bus = np.zeros((n_bus, 6))
+    bus[:, 0] = np.arange(1, n_bus + 1)
+    bus[:, 1] = 1
+    bus[gen_bus - 1, 1] = 2
+    bus[gen_bus[0] - 1, 1] = 3
+    bus[:, 2] = rng.uniform(0.0, 100.0, n_bus) * (rng.uniform(size=n_bus) < 0.8)   # Pd (rescaled by augment)
+    bus[:, 3] = bus[:, 2] * rng.uniform(-0.1, 0.5, n_bus)                           # Qd
+    gen = np.zeros((n_gen, 6))
+    gen[:, 0] = gen_bus
+    gen[:, 1] = rng.uniform(100.0, 330.0, n_gen)    # Pmax
+    gen[:, 2] = 0.0                                  # Pmin
+    gen[:, 3] = gen[:, 1] * rng.uniform(0.2, 0.7, n_gen)
+    gen[:, 4] = rng.uniform(1.0, 1.1, n_gen)        # Vg
+    gen[:, 5] = rng.uniform(-17.0, 42.0, n_gen)     # Qg
+    return _tables(bus, br, gen)
+
+
+def get_case(n_bus: int, seed: int = 0):
+    """case14 -> the IEEE table; 30/118/300 -> IEEE-sized synthetic topology (labelled)."""
+    if n_bus == 14:
+        return case14(), "IEEE case14"
+    return synthetic_case(n_bus, seed=seed), f"IEEE-sized synthetic topology ({n_bus} buses)"
+
+
+def augment(case: dict, n_samples: int, seed: int = 0):
+    """Vectorised restatement of the perturbation loop of ref GNS/augment_grids.py:35-53.
+    Returns float64 tables ``bus [S,N,13]``, ``branch [S,E,13]``, ``gen [S,Gn,21]``."""
+    rng = np.random.default_rng(seed)
+    S = int(n_samples)
+    bus = np.repeat(np.asarray(case["bus"], dtype=np.float64)[None], S, axis=0)
+    branch = np.repeat(np.asarray(case["branch"], dtype=np.float64)[None], S, axis=0)
+    gen = np.repeat(np.asarray(case["gen"], dtype=np.float64)[None], S, axis=0)
+    E, Gn, N = branch.shape[1], gen.shape[1], bus.shape[1]
+    branch[:, :, _R] *= rng.uniform(0.9, 1.1, (S, E))
+    branch[:, :, _X] *= rng.uniform(0.9, 1.1, (S, E))
+    branch[:, :, _B] *= rng.uniform(0.9, 1.1, (S, E))
+    branch[:, :, _TAP] = rng.uniform(0.8, 1.2, (S, E))
+    branch[:, :, _SHIFT] = rng.uniform(-0.2, 0.2, (S, E))
+    gen[:, :, _VG] *= rng.uniform(0.95, 1.05, (S, Gn))
+    span = gen[:, :, _PMAX] - gen[:, :, _PMIN]
+    # the reference draws Pg from U(Pmin + 0.25 span, 0.75 span)  (augment_grids.py:47-49)
+    gen[:, :, _PG] = rng.uniform(gen[:, :, _PMIN] + 0.25 * span, 0.75 * span)
+    bus[:, :, _PD] *= rng.uniform(0.5, 1.5, (S, N))
+    bus[:, :, _PD] *= (gen[:, :, _PG].sum(axis=1) / bus[:, :, _PD].sum(axis=1))[:, None]
+    bus[:, :, _QD] *= rng.uniform(0.5, 1.5, (S, N))
+    return {"baseMVA": float(case["baseMVA"]), "bus": bus, "branch": branch, "gen": gen}
+
+
+def pack_grids(bus, branch, gen, base_mva: float):
+    """Batched ``prepare_grid`` (ref GNS/utils.py:17-41), same operation order in float32:
+    cast to f32, override Gs=1 / Bs=-1, divide P,Q,Gs,Bs by baseMVA, tau==0 -> 1,
+    shift degrees -> radians, generator columns [bus, Pmax, Pmin, Pg, Vg, Qg] + copy of Pg."""
+    bus = torch.as_tensor(np.asarray(bus), dtype=torch.float32)
+    branch = torch.as_tensor(np.asarray(branch), dtype=torch.float32)
+    gen = torch.as_tensor(np.asarray(gen), dtype=torch.float32)
+    single = bus.dim() == 2
+    if single:
+        bus, branch, gen = bus[None], branch[None], gen[None]
+    buses = bus[:, :, [0, 1, 2, 3, 4, 5]].clone()
+    buses[:, :, 4] = 1.0
+    buses[:, :, 5] = -1.0
+    buses[:, :, [2, 3, 4, 5]] /= base_mva
+    lines = branch[:, :, [0, 1, 2, 3, 4, 8, 9]].clone()
+    lines[:, :, 5] = torch.where(lines[:, :, 5] == 0, torch.ones_like(lines[:, :, 5]), lines[:, :, 5])
+    lines[:, :, 6] = torch.deg2rad(lines[:, :, 6])
+    generators = gen[:, :, [0, 8, 9, 1, 5, 2]].clone()
+    generators = torch.cat((generators, generators[:, :, 3:4]), dim=2)
+    generators[:, :, [1, 2, 3, 5, 6]] /= base_mva
+    if single:
+        return buses[0], lines[0], generators[0]
+    return buses, lines, generators
+
+
+def make_batch(n_bus: int, n_samples: int, seed: int = 0, topo_seed: int = 0):
+    """Synthetic load-perturbed batch of the named case, packed: (buses, lines, generators, label)."""
+    case, label = get_case(n_bus, seed=topo_seed)
+    aug = augment(case, n_samples, seed=seed)
+    b, l, g = pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
+    return b, l, g, label

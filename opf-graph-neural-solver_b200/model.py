@@ -1,0 +1,233 @@
+"""``GNS`` - the reference's ``nn.Module`` surface on the B200 kernels.
+
+Mirrors ref GNS/main.py:17-31 (``LearningBlock``) and :107-202 (``GNS``):
+
+* constructor ``GNS(latent_dim=10, hidden_dim=10, K=30, gamma=0.9, multiple_phi=False)``,
+  attributes ``multiple_phis``, ``latent_dim``, ``gamma``, ``K`` and the ``ModuleDict``s
+  ``phi_v / phi_theta / phi_m`` (or ``phi``) and ``L_theta / L_v / L_m`` keyed ``str(k)``;
+* ``state_dict`` keys ``"{net}.{k}.linear{1,2,4}.{weight,bias}"``, and the
+  k-major construction order so ``torch.manual_seed(s)`` reproduces the reference init;
+* ``forward(buses, lines, generators, B, L, G) -> (v, theta, total_loss, last_loss)``.
+
+New capability: the three tensors may carry a leading batch dimension
+(``[S,N,6] / [S,E,7] / [S,Gn,7]``, one shared topology); outputs are then ``[S,N]``,
+``[S,N]``, ``[S]``, ``[S]``.  All arithmetic happens in the sm_100a kernels behind the C
+ABI of ``include/gns_b200.h``; this file only owns parameters, shapes and autograd glue.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .plan import TopologyPlan
+
+
+def get_BLG():
+    """Column maps of the packed bus / line / generator tensors (ref GNS/utils.py:4-13)."""
+    B = {"bus_i": 0, "type": 1, "Pd": 2, "Qd": 3, "Gs": 4, "Bs": 5}
+    L = {"f_bus": 0, "t_bus": 1, "r": 2, "x": 3, "b": 4, "tau": 5, "theta": 6}
+    G = {"bus_i": 0, "Pmax": 1, "Pmin": 2, "Pg_set": 3, "vg": 4, "qg": 5, "Pg": 6}
+    return B, L, G
+
+
+class LearningBlock(nn.Module):
+    """Parameter container of one 3-layer MLP (ref GNS/main.py:17-31).  The layer names
+    ``linear1, linear2, linear4`` are part of the checkpoint contract.  Its arithmetic runs
+    inside the fused kernels; calling the block on its own is not part of the hot path."""
+
+    def __init__(self, dim_in, hidden_dim, dim_out):
+        super().__init__()
+        self.linear1 = nn.Linear(dim_in, hidden_dim)
+        self.linear2 = nn.Linear(hidden_dim, hidden_dim)
+        self.linear4 = nn.Linear(hidden_dim, dim_out)
+
+    def forward(self, x):  # pragma: no cover - never used by GNS.forward
+        raise RuntimeError("LearningBlock is evaluated inside the fused GNS kernels; call GNS.forward")
+
+
+class _GNSFunction(torch.autograd.Function):
+    """autograd glue: one ``gns_forward`` / one ``gns_backward`` call per step."""
+
+    @staticmethod
+    def forward(ctx, module, plan, need_grad, buses, lines, gens, flat, *params):
+        lib = _lib.load_library()
+        S, N = buses.shape[0], buses.shape[1]
+        dev = buses.device
+        K, Ld, Hd, multi = module.K, module.latent_dim, module.hidden_dim, int(module.multiple_phis)
+        nbytes = lib.gns_workspace_bytes(plan.handle, S, K, Ld, Hd, multi, int(need_grad))
+        if nbytes < 0:
+            raise RuntimeError("gns_workspace_bytes: " + _lib.last_error())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        v = torch.empty(S, N, dtype=torch.float32, device=dev)
+        theta = torch.empty(S, N, dtype=torch.float32, device=dev)
+        total = torch.empty(S, dtype=torch.float32, device=dev)
+        last = torch.empty(S, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.gns_forward(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
+                             S, K, Ld, Hd, multi, float(module.gamma),
+                             v.data_ptr(), theta.data_ptr(), total.data_ptr(), last.data_ptr(),
+                             ws.data_ptr(), nbytes, int(need_grad), stream)
+        _lib.check(rc, "gns_forward")
+        if need_grad:
+            ctx.module, ctx.plan, ctx.ws = module, plan, ws
+            ctx.save_for_backward(buses, lines, gens, flat, v)
+            ctx.shapes = [p.shape for p in params]
+        return v, theta, total, last
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_v, g_theta, g_total, g_last):
+        lib = _lib.load_library()
+        module, plan, ws = ctx.module, ctx.plan, ctx.ws
+        buses, lines, gens, flat, v = ctx.saved_tensors
+        S = buses.shape[0]
+        dev = buses.device
+        K, Ld, Hd, multi = module.K, module.latent_dim, module.hidden_dim, int(module.multiple_phis)
+
+        def ptr(t):
+            return None if t is None else t.contiguous().data_ptr()
+
+        g_total = torch.zeros(S, dtype=torch.float32, device=dev) if g_total is None else g_total.contiguous()
+        keep = [g_total]
+        for t in (g_last, g_v, g_theta):
+            keep.append(None if t is None else t.contiguous())
+        if keep[2] is not None:   # v is clamped at 0 on output (ref GNS/main.py:201): no gradient where clamped
+            keep[2] = torch.where(v > 0, keep[2], torch.zeros_like(keep[2]))
+        grad_flat = torch.empty_like(flat)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.gns_backward(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
+                              S, K, Ld, Hd, multi, float(module.gamma),
+                              keep[0].data_ptr(), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
+                              grad_flat.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "gns_backward")
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = shp.numel()
+            grads.append(grad_flat[off:off + n].view(shp))
+            off += n
+        return (None, None, None, None, None, None, None) + tuple(grads)
+
+
+class GNS(nn.Module):
+    def __init__(self, latent_dim=10, hidden_dim=10, K=30, gamma=0.9, multiple_phi=False):
+        super().__init__()
+        self.multiple_phis = multiple_phi
+        if self.multiple_phis:
+            self.phi_v = nn.ModuleDict()
+            self.phi_theta = nn.ModuleDict()
+            self.phi_m = nn.ModuleDict()
+        else:
+            self.phi = nn.ModuleDict()
+        self.L_theta = nn.ModuleDict()
+        self.L_v = nn.ModuleDict()
+        self.L_m = nn.ModuleDict()
+        # k-major construction keeps the RNG stream of the reference ctor (ref GNS/main.py:124-134)
+        for k in range(K):
+            key = str(k)
+            if self.multiple_phis:
+                self.phi_v[key] = LearningBlock(5 + latent_dim, hidden_dim, latent_dim)
+                self.phi_theta[key] = LearningBlock(5 + latent_dim, hidden_dim, latent_dim)
+                self.phi_m[key] = LearningBlock(5 + latent_dim, hidden_dim, latent_dim)
+            else:
+                self.phi[key] = LearningBlock(5 + latent_dim, hidden_dim, 1)
+            self.L_theta[key] = LearningBlock(4 + 2 * latent_dim, hidden_dim, 1)
+            self.L_v[key] = LearningBlock(4 + 2 * latent_dim, hidden_dim, 1)
+            self.L_m[key] = LearningBlock(4 + 2 * latent_dim, hidden_dim, latent_dim)
+        self.latent_dim = latent_dim
+        self.hidden_dim = hidden_dim
+        self.gamma = gamma
+        self.K = K
+        # --- not part of the reference surface ---
+        self.validate_topology = True     # device-side check that a batch shares the plan's topology
+        self._flat = None                 # flat float32 parameter storage, state_dict order
+        self._plans = {}                  # topology key -> TopologyPlan
+        self._last_plan = None
+
+    # ------------------------------------------------------------------ parameters
+    def _flat_ok(self):
+        f = self._flat
+        if f is None:
+            return False
+        base, off = f.data_ptr(), 0
+        for p in self.parameters():
+            if p.device != f.device or p.dtype != torch.float32 or p.data_ptr() != base + 4 * off \
+                    or not p.is_contiguous():
+                return False
+            off += p.numel()
+        return off == f.numel()
+
+    def flatten_parameters(self):
+        """Re-home every parameter as a view of one flat float32 buffer in ``state_dict`` order
+        (what the C ABI consumes).  Called lazily; ``load_state_dict`` / in-place optimizer
+        updates keep the views intact, ``.to()`` / ``.cuda()`` trigger a re-flatten."""
+        params = list(self.parameters())
+        dev = params[0].device
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params])
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+        self._flat = flat
+        assert flat.device == dev
+        return flat
+
+    def flat_parameters(self) -> torch.Tensor:
+        if not self._flat_ok():
+            self.flatten_parameters()
+        return self._flat
+
+    # ------------------------------------------------------------------ topology plans
+    def plan_for(self, lines: torch.Tensor, generators: torch.Tensor, n_bus: int) -> TopologyPlan:
+        dev_index = lines.device.index if lines.device.index is not None else torch.cuda.current_device()
+        plan = self._last_plan
+        if plan is not None and plan.device == dev_index and \
+                (plan.n_bus, plan.n_line, plan.n_gen) == (n_bus, lines.shape[1], generators.shape[1]):
+            if not self.validate_topology or plan.matches(lines, generators):
+                return plan
+        plan = TopologyPlan.from_tensors(lines, generators, n_bus, dev_index)
+        plan = self._plans.setdefault((dev_index,) + plan.key(), plan)
+        if self.validate_topology and not plan.matches(lines, generators):
+            raise ValueError("all grids of a batch must share one topology (f_bus, t_bus, generator buses)")
+        self._last_plan = plan
+        return plan
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, buses, lines, generators, B=None, L=None, G=None):
+        """Same call as ref GNS/main.py:140.  ``B, L, G`` are accepted for compatibility; the
+        column order is fixed exactly as in the reference, which hard-codes ``lines[:, 1]`` and
+        ``lines[:, 2:]`` (ref GNS/main.py:153,155)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("GNS (B200 build) needs a CUDA device: there is no CPU fallback path")
+        single = buses.dim() == 2
+        if single:
+            buses, lines, generators = buses[None], lines[None], generators[None]
+        if buses.dim() != 3 or buses.shape[2] != 6 or lines.shape[2] != 7 or generators.shape[2] != 7:
+            raise ValueError("expected buses [S,N,6], lines [S,E,7], generators [S,Gn,7]")
+        if not (buses.shape[0] == lines.shape[0] == generators.shape[0]):
+            raise ValueError("batch sizes of buses / lines / generators differ")
+        if buses.requires_grad or lines.requires_grad or generators.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the grid tensors are not provided (the reference never uses them)")
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda":
+            self.to(torch.device("cuda", torch.cuda.current_device()))
+            p0 = next(self.parameters())
+        dev, in_dev = p0.device, buses.device
+
+        def prep(t):
+            return t.detach().to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+        buses_d, lines_d, gens_d = prep(buses), prep(lines), prep(generators)
+        with torch.cuda.device(dev):
+            flat = self.flat_parameters()
+            plan = self.plan_for(lines_d, gens_d, buses_d.shape[1])
+            params = list(self.parameters())
+            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+            v, theta, total, last = _GNSFunction.apply(self, plan, need_grad, buses_d, lines_d, gens_d, flat, *params)
+        if in_dev != dev:
+            v, theta, total, last = (t.to(in_dev) for t in (v, theta, total, last))
+        if single:
+            return v[0], theta[0], total[0], last[0]
+        return v, theta, total, last

@@ -1,0 +1,129 @@
+"""GPU parity of the forward kernel, through the module -> ctypes -> C ABI path."""
+import numpy as np
+import pytest
+import torch
+
+import opf_graph_neural_solver_b200 as pkg
+from oracle import gns_oracle as orc
+from helpers import assert_bus_close, assert_loss_close, golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+BLG = pkg.get_BLG()
+
+
+def _model_from(params, latent_dim, hidden_dim, K, gamma, multiple_phi):
+    m = pkg.GNS(latent_dim=latent_dim, hidden_dim=hidden_dim, K=K, gamma=gamma, multiple_phi=multiple_phi)
+    m.load_state_dict(params)
+    return m.cuda()
+
+
+def _check_against_oracle(model, buses, lines, gens, what):
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    want = orc.gns_forward(params, buses.double(), lines.double(), gens.double(), K=model.K,
+                           latent_dim=model.latent_dim, gamma=model.gamma, multiple_phi=model.multiple_phis)
+    with torch.no_grad():
+        got = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    assert_bus_close(got[0], want[0], what + " v")
+    assert_bus_close(got[1], want[1], what + " theta")
+    assert_loss_close(got[2], want[2], what + " total_loss")
+    assert_loss_close(got[3], want[3], what + " last_loss")
+    return got
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("ref_case14_")[-1][:-4])
+def test_forward_matches_reference_golden(lib, path):
+    g = load_golden(path)
+    model = _model_from(g["params"], g["latent_dim"], g["hidden_dim"], g["K"], g["gamma"], g["multiple_phi"])
+    with torch.no_grad():
+        v, th, tot, last = model(g["buses"].cuda(), g["lines"].cuda(), g["gens"].cuda(), *BLG)
+    assert_bus_close(v, g["v"], "v")
+    assert_bus_close(th, g["theta"], "theta")
+    assert_loss_close(tot, g["total_loss"], "total_loss")
+    assert_loss_close(last, g["last_loss"], "last_loss")
+
+
+def test_single_grid_call_has_reference_shapes_and_cpu_round_trip(lib):
+    g = load_golden([p for p in golden_files() if p.endswith("k4_l20_multi.npz")][0])
+    model = _model_from(g["params"], 20, 10, 4, 0.9, True)
+    with torch.no_grad():   # CPU tensors in (the reference's usage) -> CPU tensors out
+        v, th, tot, last = model(g["buses"][1], g["lines"][1], g["gens"][1], *BLG)
+    assert v.shape == (14,) and th.shape == (14,) and tot.shape == () and last.shape == ()
+    assert v.device.type == "cpu"
+    assert_bus_close(v, g["v"][1], "v")
+    assert_loss_close(tot, g["total_loss"][1], "total")
+    # keyword call like ref GNS/main.py:281
+    with torch.no_grad():
+        out = model(buses=g["buses"][1], lines=g["lines"][1], generators=g["gens"][1], B=BLG[0], L=BLG[1], G=BLG[2])
+    assert torch.equal(out[0], v)
+
+
+@pytest.mark.parametrize("n_bus,S", [(14, 1), (14, 37), (30, 101), (118, 19), (300, 7), (300, 297)])
+def test_forward_synthetic_cases_vs_oracle(lib, n_bus, S):
+    """ragged batch sizes (tail CTA batches), every IEEE size, seed-0 weights."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(n_bus, S, seed=5)
+    _check_against_oracle(model, buses, lines, gens, f"case{n_bus} S={S}")
+
+
+@pytest.mark.parametrize("vg,ngq", [(1, 1), (2, 1), (1, 4), (2, 8), (2, 16)])
+def test_forward_is_independent_of_launch_geometry(lib, monkeypatch, vg, ngq):
+    monkeypatch.setenv("GNS_FWD_VG", str(vg))
+    monkeypatch.setenv("GNS_FWD_NGQ", str(ngq))
+    torch.manual_seed(1)
+    model = pkg.GNS(latent_dim=10, hidden_dim=10, K=3, gamma=0.9, multiple_phi=False).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(14, 53, seed=2)
+    _check_against_oracle(model, buses, lines, gens, f"VG={vg} NGQ={ngq}")
+
+
+def test_both_lambda_arms_are_exercised(lib):
+    """ref GNS/main.py:47-57: low load takes the `if` arms, nominal load the `else` arms."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(30, 64, seed=9)
+    lo = buses.clone(); lo[:, :, 2] *= 0.3
+    hi = buses.clone(); hi[:, :, 2] *= 3.0
+    mixed = torch.cat([lo[:32], hi[32:]])
+    _check_against_oracle(model, mixed, lines, gens, "mixed lambda arms")
+
+
+def test_stress_config_k8_l64(lib):
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=64, hidden_dim=10, K=8, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(300, 5, seed=3)
+    _check_against_oracle(model, buses, lines, gens, "case300 K=8 L=64")
+
+
+def test_duplicate_generator_buses_sum_like_the_reference(lib):
+    """quirk Q7: two generators on one bus add their vg / Pg (ref GNS/main.py:146-151)."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=2, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(14, 6, seed=4)
+    gens = gens.clone(); gens[:, 1, 0] = gens[:, 0, 0]
+    _check_against_oracle(model, buses, lines, gens, "duplicate gen bus")
+
+
+def test_heterogeneous_topology_in_a_batch_is_rejected(lib):
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=2, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(14, 4, seed=4)
+    lines = lines.clone(); lines[2, 3, 1] = 9.0
+    with pytest.raises(ValueError, match="share one topology"):
+        model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+
+
+def test_unsupported_dims_fail_loudly(lib):
+    model = pkg.GNS(latent_dim=7, hidden_dim=3, K=2).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(14, 2, seed=4)
+    with pytest.raises(RuntimeError, match="no fallback"):
+        model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+
+
+def test_negative_voltage_is_clamped_like_the_reference(lib):
+    """ref GNS/main.py:201: v<0 -> 0 on output only."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=2, gamma=0.9, multiple_phi=True).cuda()
+    with torch.no_grad():
+        model.L_v["1"].linear4.bias.fill_(-5.0)      # drives non-generator voltages negative
+    buses, lines, gens, _ = pkg.data.make_batch(14, 3, seed=4)
+    got = _check_against_oracle(model, buses, lines, gens, "clamp")
+    assert float(got[0].min()) == 0.0

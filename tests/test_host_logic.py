@@ -1,0 +1,155 @@
+"""CPU: host-side logic - packing transform, perturbation recipe, CSR plan, module surface,
+and that the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import opf_graph_neural_solver_b200 as pkg
+from oracle import gns_oracle as orc
+from helpers import GOLDEN, golden_files, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported(lib):
+    text = open(os.path.join(ROOT, "include", "gns_b200.h")).read()
+    declared = set(re.findall(r"\b(gns_[a-z0-9_]+)\s*\(", text))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gns_b200.h but not exported"
+    assert set(pkg._lib.SYMBOLS) == declared
+    assert b"sm_100a" in lib.gns_version()
+
+
+def test_param_count_matches_reference_formula(lib):
+    assert lib.gns_param_count(4, 20, 10, 1) == 14768
+    assert lib.gns_param_count(8, 64, 10, 1) == 76704
+    assert lib.gns_param_count(4, 20, 10, 0) == 9212
+    assert lib.gns_dims_supported(20, 10) == 1 and lib.gns_dims_supported(7, 3) == 0
+
+
+def test_pack_grids_is_bit_exact_with_reference_prepare_grid():
+    z = np.load(os.path.join(GOLDEN, "case14_raw_1_4.npz"))
+    b, l, g = pkg.data.pack_grids(z["bus"], z["branch"], z["gen"], float(z["baseMVA"]))
+    assert np.array_equal(b.numpy(), z["buses"])
+    assert np.array_equal(l.numpy(), z["lines"])
+    assert np.array_equal(g.numpy(), z["gens"])
+    b1, l1, g1 = pkg.data.pack_grids(z["bus"][0], z["branch"][0], z["gen"][0], float(z["baseMVA"]))
+    assert b1.shape == (14, 6) and l1.shape == (20, 7) and g1.shape == (5, 7)
+
+
+def test_case14_table_equals_reference_pickle():
+    z = np.load(os.path.join(GOLDEN, "case14_base.npz"))
+    c = pkg.data.case14()
+    assert np.array_equal(c["bus"][:, :6], z["bus"][:, :6])
+    assert np.array_equal(c["branch"][:, [0, 1, 2, 3, 4, 8, 9]], z["branch"][:, [0, 1, 2, 3, 4, 8, 9]])
+    assert np.array_equal(c["gen"][:, [0, 8, 9, 1, 5, 2]], z["gen"][:, [0, 8, 9, 1, 5, 2]])
+
+
+def test_augment_follows_the_reference_recipe():
+    case = pkg.data.case14()
+    a = pkg.data.augment(case, 64, seed=3)
+    br0, br = case["branch"], a["branch"]
+    nz = br0[:, 2] > 0
+    assert ((br[:, nz, 2] / br0[nz, 2] >= 0.9) & (br[:, nz, 2] / br0[nz, 2] <= 1.1)).all()
+    assert ((br[:, :, 8] >= 0.8) & (br[:, :, 8] <= 1.2)).all()
+    assert (np.abs(br[:, :, 9]) <= 0.2).all()
+    span = case["gen"][:, 8] - case["gen"][:, 9]
+    assert ((a["gen"][:, :, 1] >= 0.25 * span - 1e-9) & (a["gen"][:, :, 1] <= 0.75 * span + 1e-9)).all()
+    np.testing.assert_allclose(a["bus"][:, :, 2].sum(1), a["gen"][:, :, 1].sum(1), rtol=1e-12)   # sum Pd == sum Pg
+    assert np.array_equal(a["branch"][:, :, :2], np.repeat(br0[None, :, :2], 64, 0))              # topology untouched
+    again = pkg.data.augment(case, 64, seed=3)
+    assert np.array_equal(again["bus"], a["bus"])                                                   # seeded
+
+
+@pytest.mark.parametrize("n_bus", [30, 118, 300])
+def test_synthetic_case_sizes_and_preconditions(n_bus):
+    c = pkg.data.synthetic_case(n_bus, seed=0)
+    E, Gn = pkg.data.IEEE_SIZES[n_bus]
+    assert c["bus"].shape == (n_bus, 13) and c["branch"].shape == (E, 13) and c["gen"].shape == (Gn, 21)
+    f, t = c["branch"][:, 0].astype(int), c["branch"][:, 1].astype(int)
+    assert f.min() >= 1 and t.max() <= n_bus and (f != t).all()
+    assert len(set(c["gen"][:, 0].astype(int))) == Gn
+    assert set(np.concatenate([f, t])) == set(range(1, n_bus + 1))        # connected spanning tree touches all
+
+
+def _host_plan(f, t, gb, n_bus):
+    return pkg.TopologyPlan(f, t, gb, n_bus, device=-1)     # host-only plan: no CUDA needed
+
+
+@pytest.mark.parametrize("n_bus", [14, 30, 118, 300])
+def test_plan_csr_is_bit_exact_against_numpy(lib, n_bus):
+    case, _ = pkg.data.get_case(n_bus)
+    f = case["branch"][:, 0].astype(np.int32) - 1
+    t = case["branch"][:, 1].astype(np.int32) - 1
+    gb = case["gen"][:, 0].astype(np.int32) - 1
+    plan = _host_plan(f, t, gb, n_bus)
+    for key, name in ((t, "in"), (f, "out")):
+        rowptr, ids = orc.csr_by(key, n_bus)
+        assert np.array_equal(plan.export(name + "_rowptr"), rowptr)
+        assert np.array_equal(plan.export(name + "_lines"), ids)
+    rowptr, ids = orc.csr_by(gb, n_bus)
+    assert np.array_equal(plan.export("gen_rowptr"), rowptr) and np.array_equal(plan.export("gen_ids"), ids)
+    in_deg = np.diff(plan.export("in_rowptr"))
+    order = orc.degree_order(in_deg)
+    assert np.array_equal(plan.export("bus_order"), order)
+    assert np.array_equal(plan.export("bus_rank")[order], np.arange(n_bus))
+
+
+def test_plan_rejects_what_the_reference_cannot_index(lib):
+    with pytest.raises(IndexError):        # bus id beyond n_bus (reference: IndexError at m[dst])
+        _host_plan([0, 1, 5], [1, 2, 0], [0], 3)
+    with pytest.raises(IndexError):        # n_bus > n_line: y_ij[src] out of range in the reference
+        _host_plan([0, 1], [1, 2], [0], 3)
+    with pytest.raises(IndexError):
+        _host_plan([], [], [], 0)
+    with pytest.raises(KeyError):
+        _host_plan([0, 1, 2], [1, 2, 0], [0], 3).export("nope")
+
+
+@pytest.mark.parametrize("multi", [True, False])
+def test_module_surface_and_state_dict_contract(multi):
+    torch.manual_seed(0)
+    m = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=multi)
+    assert m.multiple_phis is multi and m.latent_dim == 20 and m.K == 4 and m.gamma == 0.9
+    names = [n for n, _ in m.named_parameters()]
+    assert names == orc.param_names(4, multi)
+    ref = orc.init_params(20, 10, 4, multi, seed=0)
+    for n, p in m.named_parameters():
+        assert torch.equal(p.detach(), ref[n]), n            # same RNG stream as the reference ctor
+    assert sum(p.numel() for p in m.parameters()) == (14768 if multi else 9212)
+    d = pkg.GNS()                                              # reference defaults
+    assert (d.latent_dim, d.hidden_dim, d.K, d.gamma, d.multiple_phis) == (10, 10, 30, 0.9, False)
+
+
+def test_state_dict_round_trip_with_reference_checkpoint():
+    g = load_golden([p for p in golden_files() if p.endswith("k4_l20_multi.npz")][0])
+    m = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True)
+    missing = m.load_state_dict(g["params"], strict=True)     # keys saved by the reference load as they are
+    assert not missing.missing_keys and not missing.unexpected_keys
+    flat = m.flat_parameters()
+    assert flat.numel() == 14768 and m._flat_ok()
+    off = 0
+    for n, p in m.named_parameters():                          # flat buffer is in state_dict order
+        assert torch.equal(flat[off:off + p.numel()].view(p.shape), g["params"][n])
+        off += p.numel()
+    m.load_state_dict(g["params"])                             # in-place copy keeps the views
+    assert m._flat_ok()
+
+
+def test_forward_without_cuda_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    m = pkg.GNS(latent_dim=20, hidden_dim=10, K=2, multiple_phi=True)
+    g = load_golden(golden_files()[0])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(g["buses"][0], g["lines"][0], g["gens"][0], *pkg.get_BLG())
+
+
+def test_block_forward_is_not_a_side_door():
+    with pytest.raises(RuntimeError):
+        pkg.LearningBlock(3, 4, 5)(torch.zeros(1, 3))
