@@ -9,7 +9,6 @@
 
 namespace gns {
 const char* last_error_cstr();
-typedef cudaError_t (*BwdLauncher)(const struct BwdArgs& a, const Geometry& g, cudaStream_t st);
 int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const float* buses, const float* lines,
                  const float* gens, long long S, float gamma, const float* grad_total, const float* grad_last,
                  const float* grad_v, const float* grad_theta, float* grad_params, void* workspace,
@@ -169,6 +168,7 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
   a.pglob = need_grad ? reinterpret_cast<float*>(wsb + ws.pglob) : nullptr;
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.E = plan->E; a.Gn = plan->Gn; a.K = K; a.NGQ = gf.NGQ; a.G = gf.G; a.nbatch = gf.nbatch;
+  a.NGs = row_stride(plan->N * gf.G); a.EGs = row_stride(plan->E * gf.G);
   a.need_grad = need_grad ? 1 : 0;
   a.sm = gf.sm; a.to = plan->to;
   for (int k = 0; k < K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(K - k));   // ref GNS/main.py:198

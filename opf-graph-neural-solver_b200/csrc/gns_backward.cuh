@@ -1,0 +1,631 @@
+// gns_backward.cuh — persistent backward kernel: BPTT through the K steps of one CTA-batch
+// of grids, the implicit autograd backward of ref GNS/main.py:288 restated by hand.
+//
+// Per step k = K-1 .. 0 (state_k = checkpoint written by the forward kernel):
+//   1. physics adjoint: loss -> dP' -> (lambda / p_global coupling, line flows) -> v', theta'.
+//      All scatter-adds of the forward become CSR gathers here, so there are no atomics.
+//   2. MLP adjoint per bus, thread-local: the bus thread recomputes its phi / L-net
+//      activations from state_k and back-propagates them (dX), exactly mirroring the
+//      bus-centric forward.
+//   3. weight gradients (the only GEMM-shaped work): dW^T[w][o] = sum_items wide[w] * hid[o].
+//      Each warp transposes the per-item vectors of its 32 items through a private shared
+//      memory tile ([feature][item]); lane r then owns row r of dW^T and runs over the 32
+//      items with 128-bit loads (the hid rows are warp-uniform broadcasts).  State rows
+//      (v, theta, dP, dQ, m, adj m) are already stored [feature][item] and are read in place.
+//      Row sums go to a per-warp private accumulator in global memory (plain RMW, L2
+//      resident), reduced over warps by a second small kernel: deterministic, no atomics.
+#pragma once
+#include "gns_common.cuh"
+
+namespace gns {
+
+constexpr int kTS = 36;   // tile row stride in floats: 32 items + 4 (odd number of 16 B groups)
+
+struct BwdSmem {          // offsets in floats from SmemPlan.extra
+  int adj;                // [(4+L)][NGs]  adjoint of (v, theta, dP, dQ, m)
+  int nxt;                // [4][NGs]      v', theta', dP', dQ' of the state leaving the step
+  int lineg;              // [5][EGs]      per-line partials: d/dv_f, d/dv_t, d/dtheta_f, d/dD_A, d/dD_B
+  int adjD;               // [NGs]         adjoint of the alias-line angle differences
+  int tiles;              // [nwarps][trows][kTS]
+  int trows;
+  int total;
+};
+
+__host__ __device__ inline int bwd_tile_rows(int H, int PO) { return 1 + 2 * (H + 1) + 16 + PO; }
+
+__host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps) {
+  BwdSmem b{};
+  const int NGs = row_stride(N * G), EGs = row_stride(E * G);
+  int o = 0;
+  b.adj = o; o += (4 + L) * NGs;
+  b.nxt = o; o += 4 * NGs;
+  b.lineg = o; o += 5 * EGs;
+  b.adjD = o; o += NGs;
+  b.trows = bwd_tile_rows(H, PO);
+  b.tiles = o; o += nwarps * b.trows * kTS;
+  b.total = o;
+  return b;
+}
+
+struct BwdArgs {
+  const float* params;      // packed [K][wstep]
+  const float* buses; const float* lines; const float* gens;
+  const float* ckpt;        // forward checkpoints [nbatch_f][K][(4+L)*NGs_f], grid-interleaved with G_f
+  const float* pglob;       // [nbatch_f][K][G_f]
+  const float* grad_total; const float* grad_last; const float* grad_v; const float* grad_theta;
+  float* gacc;              // [ctas*nwarps][K*wstep] per-warp gradient accumulators (zeroed by the host)
+  const uint16_t* topo;
+  long long S;
+  int N, E, Gn, K, NGQ, G, nbatch;
+  int NGs, EGs;
+  int Gf, NGs_f;            // forward geometry of the checkpoints
+  SmemPlan sm;
+  BwdSmem bs;
+  TopoOffsets to;
+  float wk[kMaxK];
+};
+
+// dW^T[r][c] += sum_{item<32} row_r[item] * hid_c[item] for the lane-owned rows r = lane, lane+32, ...
+// rowfn(r) -> pointer to 32 consecutive floats (16-byte aligned); hid rows are kTS apart;
+// outfn(r, c) -> offset inside this warp's private accumulator block.
+template <int C, class RowFn, class OutFn>
+__device__ __forceinline__ void tile_gemm(int R, RowFn rowfn, const float* __restrict__ hid, float* __restrict__ g,
+                                          OutFn outfn) {
+  const int lane = threadIdx.x & 31;
+  for (int r = lane; r < R; r += 32) {
+    const float4* a4 = reinterpret_cast<const float4*>(rowfn(r));
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 2
+    for (int q = 0; q < 8; ++q) {
+      const float4 av = a4[q];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float4 h = *reinterpret_cast<const float4*>(hid + c * kTS + 4 * q);
+        acc[c] = fmaf(av.x, h.x, fmaf(av.y, h.y, fmaf(av.z, h.z, fmaf(av.w, h.w, acc[c]))));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float* p = g + outfn(r, c);
+      *p += acc[c];
+    }
+  }
+}
+
+template <int L, int H, bool MULTI, int TMAX>
+__global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) {
+  constexpr WLayout W = make_wlayout(L, H, MULTI);
+  constexpr int HP = pad4(H);
+  constexpr int PO = MULTI ? L : 1;
+  // tile row map
+  constexpr int R_ONES = 0;
+  constexpr int R_HID = 1;                 // H+1 rows
+  constexpr int R_HID2 = R_HID + H + 1;    // H+1 rows
+  constexpr int R_WIDE = R_HID2 + H + 1;   // 16 rows
+  constexpr int R_S = R_WIDE + 16;         // PO rows
+  static_assert(H + 1 + 5 <= 16, "wide staging rows");
+
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, E = a.E, Gn = a.Gn, G = a.G, NGQ = a.NGQ, K = a.K;
+  const int NG = a.NGs, EG = a.EGs, GnG = Gn * G;
+  float* const s_state = smem + a.sm.state;
+  float* const s_busc = smem + a.sm.busc;
+  float* const s_genc = smem + a.sm.genc;
+  float* const s_linef = smem + a.sm.linef;
+  float* const s_y = smem + a.sm.yline;
+  float* const s_trig = smem + a.sm.trig;
+  float* const s_red = smem + a.sm.red;
+  float* const s_w = smem + a.sm.weights;
+  uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
+  float* const s_adj = smem + a.sm.extra + a.bs.adj;
+  float* const s_nxt = smem + a.sm.extra + a.bs.nxt;
+  float* const s_lineg = smem + a.sm.extra + a.bs.lineg;
+  float* const s_adjD = smem + a.sm.extra + a.bs.adjD;
+
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int slot = tid / NGQ;
+  const int gq = tid - slot * NGQ;
+  const bool bus_on = slot < N;
+  const int n = bus_on ? slot : 0;           // safe index for idle lanes (they stage zeros, store nothing)
+  const int nb = n * G + gq;                  // offset of (bus n, grid gq) inside a [N][G] row
+  float* const tile = smem + a.sm.extra + a.bs.tiles + warp * a.bs.trows * kTS;
+  float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * W.wstep);
+
+  // zero all dynamic shared memory once: padding lanes and tail rows must hold finite values
+  for (int i = tid; i < a.sm.total_floats; i += T) smem[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < a.to.total / 2; i += T)
+    reinterpret_cast<uint32_t*>(s_topo)[i] = reinterpret_cast<const uint32_t*>(a.topo)[i];
+  tile[R_ONES * kTS + lane] = 1.f;
+  const uint16_t* const t_fi = s_topo + a.to.fi;
+  const uint16_t* const t_ti = s_topo + a.to.ti;
+  const uint16_t* const t_fa = s_topo + a.to.fa;
+  const uint16_t* const t_ta = s_topo + a.to.ta;
+  const uint16_t* const t_inp = s_topo + a.to.in_ptr;
+  const uint16_t* const t_ini = s_topo + a.to.in_ids;
+  const uint16_t* const t_outp = s_topo + a.to.out_ptr;
+  const uint16_t* const t_outi = s_topo + a.to.out_ids;
+  const uint16_t* const t_genp = s_topo + a.to.gen_ptr;
+  const uint16_t* const t_geni = s_topo + a.to.gen_ids;
+  const uint16_t* const t_ext = s_topo + a.to.ext_of;
+  const uint16_t* const t_rank = s_topo + a.to.rank_of;
+  __syncthreads();
+
+  const int e_in0 = bus_on ? t_inp[n] : 0, e_in1 = bus_on ? t_inp[n + 1] : 0;
+  const int e_out0 = bus_on ? t_outp[n] : 0, e_out1 = bus_on ? t_outp[n + 1] : 0;
+  const int j0 = bus_on ? t_genp[n] : 0, j1 = bus_on ? t_genp[n + 1] : 0;
+  const int deg = e_in1 - e_in0;
+  const float degf = (float)deg;
+  const bool is_gen = j1 > j0;
+  const int warp_max_deg = __reduce_max_sync(0xffffffffu, deg);
+
+  auto stage = [&](int row, float val) { tile[row * kTS + lane] = bus_on ? val : 0.f; };
+
+  for (int batch = blockIdx.x; batch < a.nbatch; batch += gridDim.x) {
+    const long long g0 = (long long)batch * G;
+    const long long gme = g0 + gq;                       // this thread's grid
+    const bool grid_ok = gme < a.S;
+    const long long gld = grid_ok ? gme : a.S - 1;       // replicated tail grid (zero upstream gradient)
+    const long long bf = gld / a.Gf;                     // forward CTA-batch and column of that grid
+    const int cf = (int)(gld - bf * a.Gf);
+    const size_t ck_stride = (size_t)(4 + L) * a.NGs_f;
+    const float* const ck_base = a.ckpt + (size_t)bf * K * ck_stride + cf;
+    const float gtot = grid_ok ? a.grad_total[gld] : 0.f;
+    const float glast = (grid_ok && a.grad_last) ? a.grad_last[gld] : 0.f;
+
+    // ---------------- inputs (same staging as the forward kernel) ----------------
+    load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, NG, t_rank);
+    load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, EG, nullptr);
+    load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
+    __syncthreads();
+    float part4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bus_on) {
+      part4[0] = s_busc[0 * NG + nb];
+      const float r = s_linef[0 * EG + nb], x = s_linef[1 * EG + nb];     // line id == slot here
+      s_y[nb] = 1.0f / sqrtf(r * r + x * x);
+    }
+    for (int it = tid; it < Gn * NGQ; it += T) {
+      part4[1] += s_genc[2 * GnG + it];
+      part4[2] += s_genc[1 * GnG + it];
+      part4[3] += s_genc[0 * GnG + it];
+    }
+    float tmp1[1];
+    tmp1[0] = part4[1]; block_sum_per_grid<1>(tmp1, s_red, NGQ); const float sPset = tmp1[0];
+    tmp1[0] = part4[2]; block_sum_per_grid<1>(tmp1, s_red, NGQ); const float sPmin = tmp1[0];
+    tmp1[0] = part4[3]; block_sum_per_grid<1>(tmp1, s_red, NGQ); const float sPmax = tmp1[0];
+
+    // ---------------- adjoint of the outputs; v', theta', dP', dQ' of the final state ----------------
+    if (bus_on) {
+      const int ext = t_ext[n];
+      s_adj[0 * NG + nb] = (grid_ok && a.grad_v) ? a.grad_v[gld * N + ext] : 0.f;
+      s_adj[1 * NG + nb] = (grid_ok && a.grad_theta) ? a.grad_theta[gld * N + ext] : 0.f;
+      for (int i = 2; i < 4 + L; ++i) s_adj[i * NG + nb] = 0.f;
+      const float* ck = ck_base + (size_t)(K - 1) * ck_stride + (size_t)n * a.Gf;
+      for (int i = 0; i < 4; ++i) s_nxt[i * NG + nb] = ck[(size_t)i * a.NGs_f];
+    }
+    __syncthreads();
+
+    for (int k = K - 1; k >= 0; --k) {
+      // ---------------- stage weights and state_k ----------------
+      {
+        const float4* src = reinterpret_cast<const float4*>(a.params + (size_t)k * W.wstep);
+        float4* dst = reinterpret_cast<float4*>(s_w);
+        for (int i = tid; i < W.wstep / 4; i += T) dst[i] = __ldg(src + i);
+      }
+      if (bus_on) {
+        if (k >= 1) {
+          const float* ck = ck_base + (size_t)(k - 1) * ck_stride + (size_t)n * a.Gf;
+          for (int i = 0; i < 4 + L; ++i) s_state[i * NG + nb] = ck[(size_t)i * a.NGs_f];
+        } else {   // state before step 0 (ref GNS/main.py:141-152)
+          float vv = 0.f, pg = 0.f, qg = 0.f;
+          for (int j = j0; j < j1; ++j) {
+            const int gid = t_geni[j];
+            vv += s_genc[3 * GnG + gid * G + gq];
+            pg += s_genc[5 * GnG + gid * G + gq];
+            qg += s_genc[4 * GnG + gid * G + gq];
+          }
+          vv = (vv == 0.f) ? 1.f : vv;
+          s_state[0 * NG + nb] = vv;
+          s_state[1 * NG + nb] = 0.f;
+          s_state[2 * NG + nb] = pg - s_busc[0 * NG + nb] - s_busc[2 * NG + nb] * (vv * vv);
+          s_state[3 * NG + nb] = qg - s_busc[1 * NG + nb] + s_busc[3 * NG + nb] * (vv * vv);
+          for (int i = 0; i < L; ++i) s_state[(4 + i) * NG + nb] = 0.f;
+        }
+      }
+
+      // ---------------- physics adjoint (a): dP' adjoint, lambda coupling, alias-line trig ----------------
+      const float pglob = a.pglob[((size_t)bf * K + k) * a.Gf + cf];
+      const bool lo_branch = pglob < sPset;
+      const float lam = lo_branch ? (pglob - sPmin) / (2.f * (sPset - sPmin))
+                                  : (pglob - 2.f * sPset + sPmax) / (2.f * (sPmax - sPset));
+      const bool lo_arm = lam < 0.5f;
+      float gdP = 0.f, vprime = 0.f, Gs = 0.f;
+      float part[1] = {0.f};
+      if (bus_on) {
+        const float coef = (gtot * a.wk[k] + ((k == K - 1) ? glast : 0.f)) * (2.0f / (float)N);
+        gdP = s_adj[2 * NG + nb] + coef * s_nxt[2 * NG + nb];
+        s_adj[2 * NG + nb] = gdP;                       // published for the line phase (upstream of p_from / p_to)
+        float cs = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          const int gid = t_geni[j];
+          const float Pmax = s_genc[0 * GnG + gid * G + gq], Pmin = s_genc[1 * GnG + gid * G + gq];
+          const float Pset = s_genc[2 * GnG + gid * G + gq];
+          cs += lo_arm ? 2.f * (Pset - Pmin) : 2.f * (Pmax - Pset);
+        }
+        part[0] = gdP * cs;
+        vprime = s_nxt[0 * NG + nb];
+        Gs = s_busc[2 * NG + nb];
+        // alias line j == slot: D_j = theta'[f_j] - theta'[t_j]
+        const float d = s_nxt[1 * NG + (int)t_fi[n] * G + gq] - s_nxt[1 * NG + (int)t_ti[n] * G + gq];
+        float sd, cd;
+        fast_sincos(d, sd, cd);
+        s_trig[0 * NG + nb] = d; s_trig[1 * NG + nb] = sd; s_trig[2 * NG + nb] = cd;
+      }
+      block_sum_per_grid<1>(part, s_red, NGQ);      // its barriers also publish s_w, s_state, s_trig, gdP
+      const float adj_pg = part[0] / (lo_branch ? 2.f * (sPset - sPmin) : 2.f * (sPmax - sPset));
+
+      // ---------------- physics adjoint (b): per-line partials ----------------
+      for (int it = tid; it < E * NGQ; it += T) {
+        const int e = it / NGQ;
+        const int fi = t_fi[e], ti = t_ti[e], fa = t_fa[e], ta = t_ta[e];
+        const float vf = s_nxt[0 * NG + fi * G + gq], vt = s_nxt[0 * NG + ti * G + gq];
+        const float thf = s_nxt[1 * NG + fi * G + gq], tht = s_nxt[1 * NG + ti * G + gq];
+        const float g_pf = s_adj[2 * NG + ti * G + gq];      // p_from lands on the receiving bus
+        const float g_pt = s_adj[2 * NG + fi * G + gq];      // p_to lands on the sending bus
+        const float Yf = s_y[fa * G + gq], tauf = s_linef[3 * EG + fa * G + gq], shf = s_linef[4 * EG + fa * G + gq];
+        const float Df = s_trig[0 * NG + fa * G + gq], sDf = s_trig[1 * NG + fa * G + gq], cDf = s_trig[2 * NG + fa * G + gq];
+        const float Yt = s_y[ta * G + gq], taut = s_linef[3 * EG + ta * G + gq], sht = s_linef[4 * EG + ta * G + gq];
+        const float DB = s_trig[0 * NG + ta * G + gq], sDB = s_trig[1 * NG + ta * G + gq], cDB = s_trig[2 * NG + ta * G + gq];
+        const float a1 = thf - tht - Df - shf;
+        const float a2 = tht - thf - Df + shf;
+        const float a3 = tht - thf + DB - sht;               // delta_ji[dst] = -D_B
+        float s1, c1, s2, c2, s3, c3;
+        fast_sincos(a1, s1, c1);
+        fast_sincos(a2, s2, c2);
+        fast_sincos(a3, s3, c3);
+        const float yft = Yf / tauf, yftt = Yf / (tauf * tauf), ytt = Yt / taut;
+        const float t1 = vf * vt * yft, u1 = vt * vf * ytt;
+        const float sDt = -sDB;
+        const float ss = s1 + s2;
+        const float inner = t1 * ss + vf * yftt * sDf + vt * vt * Yf * sDf;       // |.| of ref GNS/main.py:41
+        const float g_in = adj_pg * ((inner > 0.f) ? 1.f : ((inner < 0.f) ? -1.f : 0.f));
+        const float gvf = g_in * (vt * yft * ss + yftt * sDf) + g_pf * (vt * yft * s1 + 2.f * vf * yftt * sDf) +
+                          g_pt * (vt * ytt * s3);
+        const float gvt = g_in * (vf * yft * ss + 2.f * vt * Yf * sDf) + g_pf * (vf * yft * s1) +
+                          g_pt * (vf * ytt * s3 + 2.f * vt * Yt * sDt);
+        const float G1 = (g_in + g_pf) * t1 * c1, G2 = g_in * t1 * c2, G3 = g_pt * u1 * c3;
+        const float gth = G1 - G2 - G3;
+        const float gDA = -G1 - G2 + (g_in * (vf * yftt + vt * vt * Yf) + g_pf * vf * vf * yftt) * cDf;
+        const float gDB = G3 - g_pt * vt * vt * Yt * cDB;
+        const int eo = e * G + gq;
+        s_lineg[0 * EG + eo] = gvf;
+        s_lineg[1 * EG + eo] = gvt;
+        s_lineg[2 * EG + eo] = gth;
+        s_lineg[3 * EG + eo] = gDA;
+        s_lineg[4 * EG + eo] = gDB;
+      }
+      __syncthreads();
+
+      // ---------------- physics adjoint (c): CSR gathers replace the forward scatter-adds ----------------
+      float adjv = 0.f, adjth = 0.f;
+      if (bus_on) {
+        float sv = 0.f, sth = 0.f, sD = 0.f;
+        for (int e = e_out0; e < e_out1; ++e) {
+          const int eo = (int)t_outi[e] * G + gq;
+          sv += s_lineg[0 * EG + eo]; sth += s_lineg[2 * EG + eo]; sD += s_lineg[3 * EG + eo];
+        }
+        for (int e = e_in0; e < e_in1; ++e) {
+          const int eo = (int)t_ini[e] * G + gq;
+          sv += s_lineg[1 * EG + eo]; sth -= s_lineg[2 * EG + eo]; sD += s_lineg[4 * EG + eo];
+        }
+        adjv = s_adj[0 * NG + nb] + sv + gdP * (-2.f * Gs * vprime) + adj_pg * (2.f * vprime * Gs);
+        adjth = s_adj[1 * NG + nb] + sth;
+        s_adjD[(int)t_ext[n] * G + gq] = sD;               // alias line id == external bus number
+      }
+      __syncthreads();
+      if (bus_on) {                                        // D_e = theta[f_e] - theta[t_e] for alias lines e < N
+        for (int e = e_out0; e < e_out1; ++e) { const int l = t_outi[e]; if (l < N) adjth += s_adjD[l * G + gq]; }
+        for (int e = e_in0; e < e_in1; ++e) { const int l = t_ini[e]; if (l < N) adjth -= s_adjD[l * G + gq]; }
+      }
+      // adjv / adjth now hold d loss / d v', d theta' of this thread's bus (registers).
+
+      // ---------------- MLP adjoint + weight gradients (bus-centric, warp tiles) ----------------
+      float* const gk = gacc_w + (size_t)k * W.wstep;
+      {
+        const float* st = s_state + nb;
+        const float* sm_m = st + 4 * NG;
+        float* adjrow = s_adj + nb;
+        float st4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st4[i] = st[i * NG];
+        float adj4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* rows_state = s_state + 32 * warp;          // [f][item] rows of this warp's 32 items
+        const float* rows_adj = s_adj + 32 * warp;
+        float A[H], P[H], adjA[H];
+#pragma unroll
+        for (int o = 0; o < H; ++o) { A[o] = 0.f; P[o] = 0.f; adjA[o] = 0.f; }
+
+        // forward recompute of one phi net for this bus: P and the aggregate A
+        auto phi_forward = [&](const float* wphi) {
+          {
+            float b[HP];
+            load_row<HP>(b, wphi + W.phi_b1);
+#pragma unroll
+            for (int o = 0; o < H; ++o) P[o] = b[o];
+          }
+#pragma unroll 4
+          for (int i = 0; i < L; ++i) {
+            float x[1] = {sm_m[i * NG]};
+            float (&Pv)[H][1] = reinterpret_cast<float (&)[H][1]>(P);
+            row_axpy<H, HP, 1>(Pv, x, wphi + W.phi_w1m + i * HP);
+          }
+#pragma unroll
+          for (int o = 0; o < H; ++o) A[o] = 0.f;
+          for (int e = e_in0; e < e_in1; ++e) {
+            const float* lf = s_linef + (int)t_ini[e] * G + gq;
+            const float* wp = wphi + opaque_zero();
+            float z[H][1], z2[H][1];
+#pragma unroll
+            for (int o = 0; o < H; ++o) z[o][0] = P[o];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              float x[1] = {lf[c * EG]};
+              row_axpy<H, HP, 1>(z, x, wp + W.phi_w1f + c * HP);
+            }
+            {
+              float b[HP];
+              load_row<HP>(b, wp + W.phi_b2);
+#pragma unroll
+              for (int o = 0; o < H; ++o) { z2[o][0] = b[o]; z[o][0] = lrelu(z[o][0]); }
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) row_axpy<H, HP, 1>(z2, z[j], wp + W.phi_w2 + j * HP);
+#pragma unroll
+            for (int o = 0; o < H; ++o) A[o] += lrelu(z2[o][0]);
+          }
+        };
+
+        // adjoint of one phi net given adjA: line loop, dW2 / db2 / dW1f, adjP, dW1m / db1, adj m
+        auto phi_backward = [&](const float* wphi, float* gphi) {
+          float adjP[H];
+#pragma unroll
+          for (int o = 0; o < H; ++o) adjP[o] = 0.f;
+          for (int it = 0; it < warp_max_deg; ++it) {
+            const bool live = bus_on && (it < deg);
+            const float* wp = wphi + opaque_zero();
+            float z[H][1], z2[H][1], d2[H], d1[H], feat[5];
+            const float* lf = s_linef + (int)t_ini[live ? e_in0 + it : 0] * G + gq;
+#pragma unroll
+            for (int o = 0; o < H; ++o) z[o][0] = P[o];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              feat[c] = lf[c * EG];
+              float x[1] = {feat[c]};
+              row_axpy<H, HP, 1>(z, x, wp + W.phi_w1f + c * HP);
+            }
+            float h1[H][1];
+            {
+              float b[HP];
+              load_row<HP>(b, wp + W.phi_b2);
+#pragma unroll
+              for (int o = 0; o < H; ++o) { z2[o][0] = b[o]; h1[o][0] = lrelu(z[o][0]); }
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) row_axpy<H, HP, 1>(z2, h1[j], wp + W.phi_w2 + j * HP);
+#pragma unroll
+            for (int o = 0; o < H; ++o) d2[o] = live ? adjA[o] * lrelu_grad(z2[o][0]) : 0.f;
+            {
+              float (&d2v)[H][1] = reinterpret_cast<float (&)[H][1]>(d2);
+#pragma unroll
+              for (int j = 0; j < H; ++j) {
+                float t[1] = {0.f};
+                row_dot<H, HP, 1>(t, d2v, wp + W.phi_w2 + j * HP);
+                d1[j] = t[0] * lrelu_grad(z[j][0]);
+                adjP[j] += d1[j];
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int o = 0; o < H; ++o) {
+              tile[(R_HID + o) * kTS + lane] = d2[o];
+              tile[(R_HID2 + o) * kTS + lane] = d1[o];
+              tile[(R_WIDE + o) * kTS + lane] = live ? h1[o][0] : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) tile[(R_WIDE + H + 1 + c) * kTS + lane] = live ? feat[c] : 0.f;
+            __syncwarp();
+            // dW2^T[j][o] += h1[j] d2[o];  db2[o] += d2[o]
+            tile_gemm<H>(H + 1,
+                         [&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
+                         tile + R_HID * kTS, gphi,
+                         [&](int r, int c) { return (r < H ? W.phi_w2 + r * HP : W.phi_b2) + c; });
+            // dW1f^T[c5][o] += feat[c5] d1[o]
+            tile_gemm<H>(5, [&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi,
+                         [&](int r, int c) { return W.phi_w1f + r * HP + c; });
+          }
+          __syncwarp();
+#pragma unroll
+          for (int o = 0; o < H; ++o) stage(R_HID + o, adjP[o]);
+          __syncwarp();
+          // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
+          tile_gemm<H>(L + 1,
+                       [&](int r) { return r < L ? rows_state + (4 + r) * NG : tile + R_ONES * kTS; },
+                       tile + R_HID * kTS, gphi,
+                       [&](int r, int c) { return (r < L ? W.phi_w1m + r * HP : W.phi_b1) + c; });
+          {
+            float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
+#pragma unroll 4
+            for (int i = 0; i < L; ++i) {
+              float t[1] = {0.f};
+              row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
+              if (bus_on) adjrow[(4 + i) * NG] += t[0];
+            }
+          }
+        };
+
+#pragma unroll 1
+        for (int qq = 0; qq < 3; ++qq) {
+          const int q = (qq == 0) ? 2 : qq - 1;      // m-net first: it reads adj m' before anyone adds to it
+          const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
+          const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;
+          float* gphi = gk + (MULTI ? q * W.phi_size : 0);
+          float* gln = gk + W.off_ln[0] + q * W.ln_size_s;
+          if (MULTI || qq == 0) phi_forward(wphi);
+
+          // ---- L-net forward recompute; S_i staged as wide rows of dW1 ----
+          float zL[H][1], z2L[H][1];
+          {
+            float b[HP];
+            load_row<HP>(b, wln + W.ln_b1);
+#pragma unroll
+            for (int o = 0; o < H; ++o) zL[o][0] = b[o];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { float x[1] = {st4[i]}; row_axpy<H, HP, 1>(zL, x, wln + W.ln_w1 + i * HP); }
+#pragma unroll 4
+          for (int i = 0; i < L; ++i) { float x[1] = {sm_m[i * NG]}; row_axpy<H, HP, 1>(zL, x, wln + W.ln_w1 + (4 + i) * HP); }
+          __syncwarp();
+          {
+            float (&Av)[H][1] = reinterpret_cast<float (&)[H][1]>(A);
+#pragma unroll 2
+            for (int i = 0; i < PO; ++i) {
+              float sv[1] = {degf * wphi[W.phi_b4 + i]};
+              row_dot<H, HP, 1>(sv, Av, wphi + W.phi_w4 + i * HP);
+              stage(R_S + i, sv[0]);
+              row_axpy<H, HP, 1>(zL, sv, wln + W.ln_w1 + (4 + L + i) * HP);
+            }
+          }
+          float h1L[H][1], h2L[H][1];
+          {
+            float b[HP];
+            load_row<HP>(b, wln + W.ln_b2);
+#pragma unroll
+            for (int o = 0; o < H; ++o) { z2L[o][0] = b[o]; h1L[o][0] = lrelu(zL[o][0]); }
+          }
+#pragma unroll
+          for (int j = 0; j < H; ++j) row_axpy<H, HP, 1>(z2L, h1L[j], wln + W.ln_w2 + j * HP);
+#pragma unroll
+          for (int o = 0; o < H; ++o) h2L[o][0] = lrelu(z2L[o][0]);
+
+          // ---- output layer adjoint and its weight gradient ----
+          float dh2[H][1];
+#pragma unroll
+          for (int o = 0; o < H; ++o) dh2[o][0] = 0.f;
+          if (q < 2) {
+            const float g = (q == 0) ? (is_gen ? 0.f : adjv) : adjth;
+            float gv[1] = {g};
+            row_axpy<H, HP, 1>(dh2, gv, wln + W.ln_wo);
+#pragma unroll
+            for (int o = 0; o < H; ++o) stage(R_WIDE + o, h2L[o][0]);
+            stage(R_HID, g);
+            __syncwarp();
+            // dWout[j] += g h2[j];  dbout += g      (rows = [h2 (H), ones], one column g)
+            tile_gemm<1>(H + 1,
+                         [&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
+                         tile + R_HID * kTS, gln,
+                         [&](int r, int) { return r < H ? W.ln_wo + r : W.ln_bo_s; });
+          } else {
+#pragma unroll 2
+            for (int i = 0; i < L; ++i) {
+              float gm[1] = {bus_on ? adjrow[(4 + i) * NG] : 0.f};
+              row_axpy<H, HP, 1>(dh2, gm, wln + W.ln_wo + i * HP);
+            }
+#pragma unroll
+            for (int o = 0; o < H; ++o) stage(R_HID + o, h2L[o][0]);
+            stage(R_HID + H, 1.f);
+            __syncwarp();
+            // dWout[i][j] += adjm'[i] h2[j];  dbout[i] += adjm'[i]    (rows = adj m' rows in place)
+            tile_gemm<H + 1>(L, [&](int r) { return rows_adj + (4 + r) * NG; }, tile + R_HID * kTS, gln,
+                             [&](int r, int c) { return c < H ? W.ln_wo + r * HP + c : W.ln_bo_m + r; });
+          }
+          __syncwarp();
+          // ---- second layer ----
+          float d2[H][1], d1[H][1];
+#pragma unroll
+          for (int o = 0; o < H; ++o) {
+            d2[o][0] = dh2[o][0] * lrelu_grad(z2L[o][0]);
+            stage(R_HID + o, d2[o][0]);
+            stage(R_WIDE + o, h1L[o][0]);
+          }
+          __syncwarp();
+          tile_gemm<H>(H + 1,
+                       [&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
+                       tile + R_HID * kTS, gln,
+                       [&](int r, int c) { return (r < H ? W.ln_w2 + r * HP : W.ln_b2) + c; });
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            float t[1] = {0.f};
+            row_dot<H, HP, 1>(t, d2, wln + W.ln_w2 + j * HP);
+            d1[j][0] = t[0] * lrelu_grad(zL[j][0]);
+          }
+          __syncwarp();
+          // ---- first layer: dW1^T[i][o] += x[i] d1[o] with x = [v,theta,dP,dQ, m, S], db1 += d1 ----
+#pragma unroll
+          for (int o = 0; o < H; ++o) stage(R_HID + o, d1[o][0]);
+          __syncwarp();
+          tile_gemm<H>(4 + L + PO + 1,
+                       [&](int r) {
+                         return r < 4 + L ? rows_state + r * NG
+                                          : (r < 4 + L + PO ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
+                       },
+                       tile + R_HID * kTS, gln,
+                       [&](int r, int c) { return (r < 4 + L + PO ? W.ln_w1 + r * HP : W.ln_b1) + c; });
+          __syncwarp();
+          // ---- dX of the first layer ----
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float t[1] = {0.f};
+            row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + i * HP);
+            adj4[i] += t[0];
+          }
+#pragma unroll 4
+          for (int i = 0; i < L; ++i) {
+            float t[1] = {0.f};
+            row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
+            if (bus_on) adjrow[(4 + i) * NG] += t[0];
+          }
+          if (MULTI) {
+#pragma unroll
+            for (int o = 0; o < H; ++o) adjA[o] = 0.f;
+          }
+          {
+            float (&aAv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjA);
+#pragma unroll 2
+            for (int i = 0; i < PO; ++i) {
+              float t[1] = {0.f};
+              row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + L + i) * HP);
+              stage(R_S + i, t[0]);                                  // adjoint of S_i
+              row_axpy<H, HP, 1>(aAv, t, wphi + W.phi_w4 + i * HP);
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < H; ++o) stage(R_HID + o, A[o]);
+          stage(R_HID + H, degf);
+          __syncwarp();
+          // dW4[i][j] += adjS[i] A[j];  db4[i] += deg adjS[i]
+          tile_gemm<H + 1>(PO, [&](int r) { return tile + (R_S + r) * kTS; }, tile + R_HID * kTS, gphi,
+                           [&](int r, int c) { return c < H ? W.phi_w4 + r * HP + c : W.phi_b4 + r; });
+          __syncwarp();
+          if (MULTI || qq == 2) phi_backward(wphi, gphi);
+        }
+        if (bus_on) {
+          adjrow[0 * NG] = adjv + adj4[0];
+          adjrow[1 * NG] = adjth + adj4[1];
+          adjrow[2 * NG] = adj4[2];
+          adjrow[3 * NG] = adj4[3];
+        }
+      }
+      __syncthreads();
+      // state_k's (v, theta, dP, dQ) are the primes of step k-1
+      if (bus_on && k >= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_nxt[i * NG + nb] = s_state[i * NG + nb];
+      }
+      __syncthreads();
+    }  // k
+  }  // batch
+}
+
+}  // namespace gns

@@ -17,6 +17,13 @@ constexpr int kMaxK = 64;
 constexpr float kSlope = 0.01f;  // nn.LeakyReLU default, ref GNS/main.py:23
 
 __host__ __device__ constexpr int pad4(int x) { return (x + 3) & ~3; }
+// Row stride (floats) of a [rows][items] shared-memory array: multiple of 4 (16-byte rows) with
+// an odd number of 16-byte groups, so that 128-bit reads of 8 consecutive ROWS at the same item
+// offset fall into 8 different bank groups (used by the backward weight-gradient tiles).
+__host__ __device__ constexpr int row_stride(int items) {
+  int p = pad4(items);
+  return ((p / 4) % 2 == 0) ? p + 4 : p;
+}
 
 // ---------------------------------------------------------------------------------
 // Packed per-step weight layout.  Every matrix is stored [wide][HP]: the fast index is
@@ -203,6 +210,28 @@ __device__ __forceinline__ void row_dot(float (&out)[VG], const float (&h)[H][VG
     for (int g = 0; g < VG; ++g) out[g] = fmaf(h[o][g], w[o], out[g]);
 }
 
+// ---- staged input load: reference AoS rows -> grid-interleaved SoA in shared memory ----
+// src: [S][rows][cols]; keeps columns c0..cols-1 as dst[(c-c0)][slot(row)][G] (+gl).
+__device__ __forceinline__ void load_block(const float* __restrict__ src, float* __restrict__ dst,
+                                           long long g0, long long S, int G, int rows, int cols, int c0,
+                                           int dst_stride, const uint16_t* __restrict__ slot_of_row) {
+  const int per_grid = rows * cols;
+  const int total = per_grid * G;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int gl = idx / per_grid;
+    const int rem = idx - gl * per_grid;
+    const int row = rem / cols;
+    const int c = rem - row * cols;
+    long long g = g0 + gl;
+    if (g >= S) g = S - 1;  // tail batch: replicate the last grid (results are not stored)
+    const float val = __ldg(src + g * per_grid + rem);
+    if (c >= c0) {
+      const int slot = slot_of_row ? (int)slot_of_row[row] : row;
+      dst[(c - c0) * dst_stride + slot * G + gl] = val;
+    }
+  }
+}
+
 // Deterministic per-grid block reduction.  Thread `tid` contributes x[VG] for grids
 // (tid % NGQ)*VG .. +VG.  Requires 32 % NGQ == 0 and blockDim.x % 32 == 0.
 // `red` holds nwarps*G floats.  Every thread receives the total of its own grids.
@@ -257,6 +286,7 @@ struct FwdArgs {
   const uint16_t* topo;    // index block in global memory
   long long S;
   int N, E, Gn, K, NGQ, G, nbatch;
+  int NGs, EGs;            // padded row strides of the [.][N][G] and [.][E][G] arrays
   int need_grad;
   SmemPlan sm;
   TopoOffsets to;

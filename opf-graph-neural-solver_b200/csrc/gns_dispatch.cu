@@ -14,4 +14,17 @@ FwdLauncher find_forward(int L, int H, int multi, int VG, int tmax) {
   }
   return nullptr;
 }
+BwdLauncher find_backward_l10(int multi, int tmax);
+BwdLauncher find_backward_l20(int multi, int tmax);
+BwdLauncher find_backward_l64(int multi, int tmax);
+
+BwdLauncher find_backward(int L, int H, int multi, int tmax) {
+  if (H != 10) return nullptr;
+  switch (L) {
+    case 10: return find_backward_l10(multi, tmax);
+    case 20: return find_backward_l20(multi, tmax);
+    case 64: return find_backward_l64(multi, tmax);
+  }
+  return nullptr;
+}
 }  // namespace gns

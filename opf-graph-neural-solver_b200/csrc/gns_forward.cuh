@@ -14,28 +14,6 @@
 
 namespace gns {
 
-// ---- staged input load: reference AoS rows -> grid-interleaved SoA in shared memory ----
-// src: [S][rows][cols]; keeps columns c0..cols-1 as dst[(c-c0)][slot(row)][G] (+gl).
-__device__ __forceinline__ void load_block(const float* __restrict__ src, float* __restrict__ dst,
-                                           long long g0, long long S, int G, int rows, int cols, int c0,
-                                           const uint16_t* __restrict__ slot_of_row) {
-  const int per_grid = rows * cols;
-  const int total = per_grid * G;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int gl = idx / per_grid;
-    const int rem = idx - gl * per_grid;
-    const int row = rem / cols;
-    const int c = rem - row * cols;
-    long long g = g0 + gl;
-    if (g >= S) g = S - 1;  // tail batch: replicate the last grid (results are not stored)
-    const float val = __ldg(src + g * per_grid + rem);
-    if (c >= c0) {
-      const int slot = slot_of_row ? (int)slot_of_row[row] : row;
-      dst[((c - c0) * rows + slot) * G + gl] = val;
-    }
-  }
-}
-
 template <int L, int H, bool MULTI, int VG, int TMAX>
 __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   constexpr WLayout W = make_wlayout(L, H, MULTI);
@@ -45,7 +23,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 
   extern __shared__ __align__(16) float smem[];
   const int N = a.N, E = a.E, Gn = a.Gn, G = a.G, NGQ = a.NGQ, K = a.K;
-  const int NG = N * G, EG = E * G, GnG = Gn * G;
+  const int NG = a.NGs, EG = a.EGs, GnG = Gn * G;   // padded row strides
   float* const s_state = smem + a.sm.state;
   float* const s_busc = smem + a.sm.busc;
   float* const s_genc = smem + a.sm.genc;
@@ -85,9 +63,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     const long long g0 = (long long)batch * G;
 
     // ---------------- load + de-interleave the G grids of this batch ----------------
-    load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, t_rank);
-    load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, nullptr);
-    load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, nullptr);
+    load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, NG, t_rank);
+    load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, EG, nullptr);
+    load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
     __syncthreads();
 
     // ---------------- state init (ref GNS/main.py:141-152) ----------------

@@ -65,5 +65,8 @@ const gns_plan::PackMap* get_pack_map(gns_plan* plan, const ModelDims& md);
 // kernel launchers (defined in the per-dimension translation units)
 typedef cudaError_t (*FwdLauncher)(const FwdArgs& a, const Geometry& g, cudaStream_t st);
 FwdLauncher find_forward(int L, int H, int multi, int VG, int tmax);
+struct BwdArgs;
+typedef cudaError_t (*BwdLauncher)(const BwdArgs& a, const Geometry& g, cudaStream_t st);
+BwdLauncher find_backward(int L, int H, int multi, int tmax);
 
 }  // namespace gns

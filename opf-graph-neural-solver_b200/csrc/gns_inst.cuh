@@ -2,6 +2,7 @@
 // hidden_dim 10.  Included by gns_inst_l*.cu so the variants compile in parallel.
 #pragma once
 #include "gns_forward.cuh"
+#include "gns_backward.cuh"
 #include "gns_host.h"
 
 namespace gns {
@@ -28,6 +29,29 @@ static FwdLauncher pick_forward(int multi, int VG, int tmax) {
   } else if (tmax == 1024 && VG == 1) {
     return multi ? launch_forward<L, H, true, 1, 1024> : launch_forward<L, H, false, 1, 1024>;
   }
+  return nullptr;
+}
+
+
+template <int L, int H, bool MULTI, int TMAX>
+static cudaError_t launch_backward(const BwdArgs& a, const Geometry& g, cudaStream_t st) {
+  auto kern = gns_backward_kernel<L, H, MULTI, TMAX>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, g.T, g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  // g.ctas accumulator blocks were provisioned by the host; never launch more than that
+  const int ctas = std::min(std::min(g.nbatch, occ * g.num_sms), g.ctas);
+  kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int L, int H>
+static BwdLauncher pick_backward(int multi, int tmax) {
+  if (tmax == 384) return multi ? launch_backward<L, H, true, 384> : launch_backward<L, H, false, 384>;
+  if (tmax == 1024) return multi ? launch_backward<L, H, true, 1024> : launch_backward<L, H, false, 1024>;
   return nullptr;
 }
 

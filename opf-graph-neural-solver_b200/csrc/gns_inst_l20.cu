@@ -3,4 +3,5 @@
 #include "gns_inst.cuh"
 namespace gns {
 FwdLauncher find_forward_l20(int multi, int VG, int tmax) { return pick_forward<20, 10>(multi, VG, tmax); }
+BwdLauncher find_backward_l20(int multi, int tmax) { return pick_backward<20, 10>(multi, tmax); }
 }  // namespace gns

@@ -3,4 +3,5 @@
 #include "gns_inst.cuh"
 namespace gns {
 FwdLauncher find_forward_l64(int multi, int VG, int tmax) { return pick_forward<64, 10>(multi, VG, tmax); }
+BwdLauncher find_backward_l64(int multi, int tmax) { return pick_backward<64, 10>(multi, tmax); }
 }  // namespace gns

@@ -47,13 +47,14 @@ static SmemPlan plan_smem(int N, int E, int Gn, int G, int L, int wstep, int nwa
   SmemPlan s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
-  s.state = take((4 + L) * N * G);
-  s.busc = take(4 * N * G);
+  const int NGs = row_stride(N * G), EGs = row_stride(E * G);
+  s.state = take((4 + L) * NGs);
+  s.busc = take(4 * NGs);
   s.genc = take(6 * Gn * G);
-  s.linef = take(5 * E * G);
-  s.yline = take(N * G);
-  s.trig = take(3 * N * G);
-  s.flows = take(4 * E * G);
+  s.linef = take(5 * EGs);
+  s.yline = take(NGs);
+  s.trig = take(3 * NGs);
+  s.flows = take(4 * EGs);
   s.gsum = take(4 * G);
   s.red = take(nwarps * G);
   s.weights = take(wstep);
@@ -78,8 +79,9 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
   const int target_threads = env_int("GNS_TARGET_THREADS", 320);
   for (int VG : {2, 1}) {
     if (force_vg && VG != force_vg) continue;
+    if (backward && VG != 1) continue;          // the backward kernel handles one grid per thread
     // small batches: one grid per thread so that the batch spreads over more SMs
-    if (!force_vg && VG == 2 && (S + 1) / 2 < plan->num_sms) continue;
+    if (!force_vg && !backward && VG == 2 && (S + 1) / 2 < plan->num_sms) continue;
     for (int NGQ = 32; NGQ >= 1; NGQ >>= 1) {
       if (force_ngq && NGQ != force_ngq) continue;
       const int T = ((N * NGQ + 31) / 32) * 32;
@@ -190,7 +192,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
   size_t o = 0;
   w.packed_params = o; o = align(o + (size_t)md.K * W.wstep * 4);
   if (need_grad) {
-    const size_t nst = (size_t)pad4((4 + md.L) * plan->N * fwd.G);
+    const size_t nst = (size_t)(4 + md.L) * row_stride(plan->N * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * md.K * W.wstep * 4);

@@ -1,0 +1,126 @@
+"""GPU parity of the backward kernel (hand-written BPTT) against the reference's autograd
+gradients (golden vectors) and against the oracle's autograd on larger cases."""
+import pytest
+import torch
+
+import opf_graph_neural_solver_b200 as pkg
+from oracle import gns_oracle as orc
+from helpers import assert_grads_close, assert_loss_close, golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+BLG = pkg.get_BLG()
+
+
+def _model_from(params, latent_dim, hidden_dim, K, gamma, multiple_phi):
+    m = pkg.GNS(latent_dim=latent_dim, hidden_dim=hidden_dim, K=K, gamma=gamma, multiple_phi=multiple_phi)
+    m.load_state_dict(params)
+    return m.cuda()
+
+
+def _grads(model):
+    return {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+
+
+def per_tensor_report(got, want):
+    gmax = max(float(w.abs().max()) for w in want.values())
+    rows = []
+    for n, w in want.items():
+        err = float((got[n].detach().cpu().double() - w.double()).abs().max())
+        rows.append((err / gmax, n, err, float(w.abs().max())))
+    rows.sort(reverse=True)
+    return "\n".join(f"{r[1]:32s} err {r[2]:.3e}  max|g| {r[3]:.3e}" for r in rows[:12])
+
+
+@pytest.mark.parametrize("path", [p for p in golden_files() if "l64" not in p],
+                         ids=lambda p: p.split("ref_case14_")[-1][:-4])
+def test_gradients_match_reference_autograd(lib, path):
+    g = load_golden(path)
+    model = _model_from(g["params"], g["latent_dim"], g["hidden_dim"], g["K"], g["gamma"], g["multiple_phi"])
+    v, th, tot, last = model(g["buses"].cuda(), g["lines"].cuda(), g["gens"].cuda(), *BLG)
+    tot.mean().backward()                       # training reduction, ref GNS/main.py:284-288
+    got = _grads(model)
+    try:
+        assert_grads_close(got, g["grads"], g["name"])
+    except AssertionError:
+        print(per_tensor_report(got, g["grads"]))
+        raise
+    for n in g["none_grads"]:                   # unused last-step nets: exactly zero here (None in the reference)
+        assert float(got[n].abs().max()) == 0.0, n
+
+
+@pytest.mark.parametrize("n_bus,S,multi", [(14, 5, True), (30, 33, True), (118, 9, True), (300, 3, True),
+                                            (30, 17, False), (300, 2, False)])
+def test_gradients_vs_oracle_autograd(lib, n_bus, S, multi):
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=multi).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(n_bus, S, seed=7)
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    (_, _, otot, _), want = orc.gns_loss_and_grads(params, buses.double(), lines.double(), gens.double(), K=4,
+                                                   latent_dim=20, gamma=0.9, multiple_phi=multi)
+    out = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    out[2].mean().backward()
+    assert_loss_close(out[2], otot, "total")
+    got = _grads(model)
+    try:
+        assert_grads_close(got, want, f"case{n_bus}")
+    except AssertionError:
+        print(per_tensor_report(got, want))
+        raise
+
+
+def test_gradients_of_an_arbitrary_loss_on_all_four_outputs(lib):
+    """v, theta, total_loss, last_loss all carry gradients (supervised / mixed losses)."""
+    torch.manual_seed(3)
+    model = pkg.GNS(latent_dim=10, hidden_dim=10, K=3, gamma=0.8, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(30, 11, seed=2)
+    w = [torch.randn(11), torch.randn(11), torch.randn(11, 30), torch.randn(11, 30)]
+    leaves = {n: p.detach().cpu().double().requires_grad_(True) for n, p in model.named_parameters()}
+    ov, oth, otot, olast = orc.gns_forward(leaves, buses.double(), lines.double(), gens.double(), K=3,
+                                           latent_dim=10, gamma=0.8, multiple_phi=True)
+    oloss = (otot * w[0]).sum() + (olast * w[1]).sum() + (ov * w[2]).sum() + (oth * w[3]).sum()
+    og = torch.autograd.grad(oloss, list(leaves.values()), allow_unused=True)
+    want = {n: (torch.zeros_like(p) if gr is None else gr) for (n, p), gr in zip(leaves.items(), og)}
+    v, th, tot, last = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    loss = (tot * w[0].cuda()).sum() + (last * w[1].cuda()).sum() + (v * w[2].cuda()).sum() + (th * w[3].cuda()).sum()
+    loss.backward()
+    got = _grads(model)
+    try:
+        assert_grads_close(got, want, "mixed loss")
+    except AssertionError:
+        print(per_tensor_report(got, want))
+        raise
+
+
+def test_reference_style_per_sample_loop_accumulates_like_a_batch(lib):
+    """ref GNS/main.py:279-288: per-sample forward, mean of losses, one backward."""
+    g = load_golden([p for p in golden_files() if p.endswith("k4_l20_multi.npz")][0])
+    model = _model_from(g["params"], 20, 10, 4, 0.9, True)
+    losses = []
+    for i in range(8):
+        _, _, loss, _ = model(buses=g["buses"][i], lines=g["lines"][i], generators=g["gens"][i],
+                              B=BLG[0], L=BLG[1], G=BLG[2])
+        losses.append(loss)
+    torch.stack(losses).mean().backward()
+    loop = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad()
+    out = model(g["buses"][:8].cuda(), g["lines"][:8].cuda(), g["gens"][:8].cuda(), *BLG)
+    out[2].mean().backward()
+    assert_grads_close(loop, {n: p.grad.cpu() for n, p in model.named_parameters()}, "loop vs batch")
+
+
+def test_adam_step_matches_torch(lib):
+    torch.manual_seed(0)
+    n = 14768
+    p = torch.randn(n, device="cuda"); g = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        ref.grad = g.clone()
+        opt.step()
+        rc = lib.gns_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8,
+                               step, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        g = g * 0.5 + 0.1
+    torch.cuda.synchronize()
+    assert (p - ref.detach()).abs().max() < 1e-6
