@@ -195,7 +195,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     const size_t nst = (size_t)(4 + md.L) * row_stride(plan->N * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
-    w.gpartial = o; o = align(o + (size_t)bwd.ctas * md.K * W.wstep * 4);
+    w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * W.wstep * 4);   // one block per warp
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
   }
   w.total = o;
