@@ -1,6 +1,7 @@
 // gns_backward.cu — host side of the backward pass: geometry, launch, and the two small
 // kernels that fold the per-warp gradient accumulators into the state_dict-order gradient.
 #include <algorithm>
+#include <cstring>
 
 #include "gns_backward.cuh"
 #include "gns_host.h"
@@ -83,6 +84,7 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.S = S; a.N = plan->N; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
   a.NGs = row_stride(plan->N * gb.G); a.EGs = row_stride(plan->E * gb.G);
   a.Gf = gf.G; a.NGs_f = row_stride(plan->N * gf.G);
+  std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);
   a.sm = gb.sm;
   a.bs = make_bwd_smem(plan->N, plan->E, gb.G, md.L, md.H, md.L, nwarps);
   a.to = plan->to;

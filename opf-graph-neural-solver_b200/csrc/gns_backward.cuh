@@ -59,6 +59,7 @@ struct BwdArgs {
   int N, E, Gn, K, NGQ, G, nbatch;
   int NGs, EGs;
   int Gf, NGs_f;            // forward geometry of the checkpoints
+  unsigned char grp_of_warp[32];
   SmemPlan sm;
   BwdSmem bs;
   TopoOffsets to;
@@ -125,8 +126,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   float* const s_adjD = smem + a.sm.extra + a.bs.adjD;
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-  const int slot = tid / NGQ;
-  const int gq = tid - slot * NGQ;
+  const int grp = a.grp_of_warp[warp];                 // bus group of this warp (sub-partition balancing)
+  const int slot = grp * (32 / NGQ) + lane / NGQ;
+  const int gq = lane % NGQ;
   const bool bus_on = slot < N;
   const int n = bus_on ? slot : 0;           // safe index for idle lanes (they stage zeros, store nothing)
   const int nb = n * G + gq;                  // offset of (bus n, grid gq) inside a [N][G] row
@@ -341,8 +343,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
         for (int i = 0; i < 4; ++i) st4[i] = st[i * NG];
         float adj4[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* rows_state = s_state + 32 * warp;          // [f][item] rows of this warp's 32 items
-        const float* rows_adj = s_adj + 32 * warp;
+        const float* rows_state = s_state + 32 * grp;          // [f][item] rows of this warp's 32 items
+        const float* rows_adj = s_adj + 32 * grp;
         float A[H], P[H], adjA[H];
 #pragma unroll
         for (int o = 0; o < H; ++o) { A[o] = 0.f; P[o] = 0.f; adjA[o] = 0.f; }

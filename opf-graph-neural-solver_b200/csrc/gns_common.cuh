@@ -288,6 +288,7 @@ struct FwdArgs {
   int N, E, Gn, K, NGQ, G, nbatch;
   int NGs, EGs;            // padded row strides of the [.][N][G] and [.][E][G] arrays
   int need_grad;
+  unsigned char grp_of_warp[32];   // warp -> group of 32/NGQ consecutive bus slots
   SmemPlan sm;
   TopoOffsets to;
   float wk[kMaxK];         // gamma^(K-k) rounded to float like the reference's python scalar

@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
 
   const int tid = threadIdx.x, T = blockDim.x;
-  const int slot = tid / NGQ;           // bus slot (internal order) in bus phases
-  const int gq = tid - slot * NGQ;
+  // bus slot (internal order) in bus phases; the warp -> bus-group map balances the 4 sub-partitions
+  const int slot = (int)a.grp_of_warp[tid >> 5] * (32 / NGQ) + (tid & 31) / NGQ;
+  const int gq = (tid & 31) % NGQ;
   const int gcol = gq * VG;
   const bool bus_on = slot < N;
 

@@ -37,6 +37,7 @@ struct Geometry {
   int nbatch = 0, ctas = 0, num_sms = 0;
   size_t smem_bytes = 0;
   SmemPlan sm{};
+  unsigned char grp_of_warp[32] = {0};   // bus group handled by each warp (balances the 4 SM sub-partitions)
 };
 
 struct ModelDims { int K, L, H, multi; };

@@ -68,6 +68,38 @@ static SmemPlan plan_smem(int N, int E, int Gn, int G, int L, int wstep, int nwa
 // extra shared memory of the backward kernel, in floats (see gns_backward.cuh)
 int backward_extra_floats(int N, int E, int G, int L, int H, int T);
 
+// Warp w runs on SM sub-partition w % 4.  A warp's bus phase costs ~ (1 + 0.15 * max in-degree of
+// its bus group), so groups are placed longest-first on the sub-partition with the least load
+// that still has a free warp.
+static void balance_warps(const gns_plan* plan, Geometry* g) {
+  const int nw = g->T / 32, spw = 32 / g->NGQ;
+  std::vector<std::pair<float, int>> cost(nw);
+  for (int grp = 0; grp < nw; ++grp) {
+    int mx = -1;
+    for (int s = grp * spw; s < std::min((grp + 1) * spw, plan->N); ++s) {
+      const int b = plan->bus_order[s];
+      mx = std::max(mx, plan->in_rowptr[b + 1] - plan->in_rowptr[b]);
+    }
+    cost[grp] = {mx < 0 ? 0.f : 1.f + 0.15f * mx, grp};
+  }
+  std::stable_sort(cost.begin(), cost.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+  float load[4] = {0, 0, 0, 0};
+  int used[4] = {0, 0, 0, 0};
+  for (const auto& c : cost) {
+    int best = -1;
+    for (int sp = 0; sp < 4; ++sp) {
+      const int cap = (nw - sp + 3) / 4;           // warps sp, sp+4, ...
+      if (used[sp] >= cap) continue;
+      if (best < 0 || load[sp] < load[best]) best = sp;
+    }
+    const int warp = best + 4 * used[best];
+    used[best]++;
+    load[best] += c.first;
+    g->grp_of_warp[warp] = (unsigned char)c.second;
+  }
+  if (std::getenv("GNS_NO_BALANCE")) for (int w = 0; w < nw; ++w) g->grp_of_warp[w] = (unsigned char)w;
+}
+
 bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, bool backward, Geometry* out) {
   const int N = plan->N, E = plan->E, Gn = plan->Gn;
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
@@ -98,6 +130,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       const size_t bytes = (size_t)sm.total_floats * 4;
       if ((int)bytes > limit) continue;
       g.smem_bytes = bytes; g.sm = sm;
+      balance_warps(plan, &g);
       g.nbatch = (int)nb; g.num_sms = plan->num_sms;
       best = g; found = true;
       break;
