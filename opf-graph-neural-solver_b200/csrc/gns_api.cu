@@ -167,8 +167,8 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
   a.ckpt = need_grad ? reinterpret_cast<float*>(wsb + ws.ckpt) : nullptr;
   a.pglob = need_grad ? reinterpret_cast<float*>(wsb + ws.pglob) : nullptr;
   a.topo = plan->d_topo;
-  a.S = S; a.N = plan->N; a.E = plan->E; a.Gn = plan->Gn; a.K = K; a.NGQ = gf.NGQ; a.G = gf.G; a.nbatch = gf.nbatch;
-  a.NGs = row_stride(plan->N * gf.G); a.EGs = row_stride(plan->E * gf.G);
+  a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = K; a.NGQ = gf.NGQ; a.G = gf.G; a.nbatch = gf.nbatch;
+  a.NGs = row_stride(plan->Ns * gf.G); a.EGs = row_stride(plan->E * gf.G);
   a.need_grad = need_grad ? 1 : 0;
   std::memcpy(a.grp_of_warp, gf.grp_of_warp, 32);
   a.sm = gf.sm; a.to = plan->to;

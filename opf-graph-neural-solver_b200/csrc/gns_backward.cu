@@ -81,12 +81,12 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.grad_total = grad_total; a.grad_last = grad_last; a.grad_v = grad_v; a.grad_theta = grad_theta;
   a.gacc = gacc;
   a.topo = plan->d_topo;
-  a.S = S; a.N = plan->N; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
-  a.NGs = row_stride(plan->N * gb.G); a.EGs = row_stride(plan->E * gb.G);
-  a.Gf = gf.G; a.NGs_f = row_stride(plan->N * gf.G);
+  a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
+  a.NGs = row_stride(plan->Ns * gb.G); a.EGs = row_stride(plan->E * gb.G);
+  a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G);
   std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);
   a.sm = gb.sm;
-  a.bs = make_bwd_smem(plan->N, plan->E, gb.G, md.L, md.H, md.L, nwarps);
+  a.bs = make_bwd_smem(plan->Ns, plan->E, gb.G, md.L, md.H, md.L, nwarps);
   a.to = plan->to;
   for (int k = 0; k < md.K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(md.K - k));
   e = launch(a, gb, st);

@@ -31,7 +31,7 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
   int total;
 };
 
-__host__ __device__ inline int bwd_tile_rows(int H, int PO) { return 1 + 2 * (H + 1) + 16 + PO; }
+__host__ __device__ inline int bwd_tile_rows(int H, int PO) { return 1 + (H + 1) + 16 + (PO > H + 1 ? PO : H + 1); }
 
 __host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps) {
   BwdSmem b{};
@@ -56,7 +56,7 @@ struct BwdArgs {
   float* gacc;              // [ctas*nwarps][K*wstep] per-warp gradient accumulators (zeroed by the host)
   const uint16_t* topo;
   long long S;
-  int N, E, Gn, K, NGQ, G, nbatch;
+  int N, Ns, E, Gn, K, NGQ, G, nbatch;
   int NGs, EGs;
   int Gf, NGs_f;            // forward geometry of the checkpoints
   unsigned char grp_of_warp[32];
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   // tile row map
   constexpr int R_ONES = 0;
   constexpr int R_HID = 1;                 // H+1 rows
-  constexpr int R_HID2 = R_HID + H + 1;    // H+1 rows
-  constexpr int R_WIDE = R_HID2 + H + 1;   // 16 rows
-  constexpr int R_S = R_WIDE + 16;         // PO rows
+  constexpr int R_WIDE = R_HID + H + 1;    // 16 rows
+  constexpr int R_S = R_WIDE + 16;         // max(PO, H+1) rows: S_i / adjoint of S_i ...
+  constexpr int R_HID2 = R_S;              // ... and, once those are dead (phi adjoint), a second hid block
   static_assert(H + 1 + 5 <= 16, "wide staging rows");
 
   extern __shared__ __align__(16) float smem[];
@@ -129,9 +129,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const int grp = a.grp_of_warp[warp];                 // bus group of this warp (sub-partition balancing)
   const int slot = grp * (32 / NGQ) + lane / NGQ;
   const int gq = lane % NGQ;
-  const bool bus_on = slot < N;
-  const int n = bus_on ? slot : 0;           // safe index for idle lanes (they stage zeros, store nothing)
-  const int nb = n * G + gq;                  // offset of (bus n, grid gq) inside a [N][G] row
+  const bool slot_on = slot < a.Ns;           // owns a bus slot (primary or twin)
   float* const tile = smem + a.sm.extra + a.bs.tiles + warp * a.bs.trows * kTS;
   float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * W.wstep);
 
@@ -145,21 +143,37 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const uint16_t* const t_ti = s_topo + a.to.ti;
   const uint16_t* const t_fa = s_topo + a.to.fa;
   const uint16_t* const t_ta = s_topo + a.to.ta;
-  const uint16_t* const t_inp = s_topo + a.to.in_ptr;
+  const uint16_t* const t_inb = s_topo + a.to.in_b;
+  const uint16_t* const t_ine = s_topo + a.to.in_e;
+  const uint16_t* const t_infe = s_topo + a.to.in_fe;
   const uint16_t* const t_ini = s_topo + a.to.in_ids;
-  const uint16_t* const t_outp = s_topo + a.to.out_ptr;
+  const uint16_t* const t_outb = s_topo + a.to.out_b;
+  const uint16_t* const t_oute = s_topo + a.to.out_e;
   const uint16_t* const t_outi = s_topo + a.to.out_ids;
-  const uint16_t* const t_genp = s_topo + a.to.gen_ptr;
+  const uint16_t* const t_genb = s_topo + a.to.gen_b;
+  const uint16_t* const t_gene = s_topo + a.to.gen_e;
   const uint16_t* const t_geni = s_topo + a.to.gen_ids;
   const uint16_t* const t_ext = s_topo + a.to.ext_of;
   const uint16_t* const t_rank = s_topo + a.to.rank_of;
+  const uint16_t* const t_prim = s_topo + a.to.prim_of;
+  const uint16_t* const t_gsz = s_topo + a.to.gsz;
   __syncthreads();
 
-  const int e_in0 = bus_on ? t_inp[n] : 0, e_in1 = bus_on ? t_inp[n + 1] : 0;
-  const int e_out0 = bus_on ? t_outp[n] : 0, e_out1 = bus_on ? t_outp[n + 1] : 0;
-  const int j0 = bus_on ? t_genp[n] : 0, j1 = bus_on ? t_genp[n + 1] : 0;
-  const int deg = e_in1 - e_in0;
-  const float degf = (float)deg;
+  // slot bookkeeping: a bus's state / adjoint live in its primary slot; twins only help with its lines
+  const int sl = slot_on ? slot : 0;
+  const int n = t_prim[sl];                             // primary slot of this slot's bus
+  const bool bus_on = slot_on && n == sl;               // this thread owns the bus
+  const int nb = n * G + gq;                            // offset of (bus, grid gq) inside a [Ns][G] row
+  const int jb = slot * G + gq;                         // offset when `slot` is used as an alias LINE id (< N)
+  const int gsz = slot_on ? (int)t_gsz[sl] : 1;
+  const bool warp_has_twins = __any_sync(0xffffffffu, gsz > 1);
+  const int leader_lane = lane - (sl - n) * NGQ;        // lane of the primary slot of this twin group
+  const int e_in0 = slot_on ? (int)t_inb[sl] : 0, e_in1 = slot_on ? (int)t_ine[sl] : 0;   // lines this slot walks
+  const int e_full1 = bus_on ? (int)t_infe[sl] : e_in0;                                     // end of the bus's in-list
+  const int e_out0 = bus_on ? (int)t_outb[sl] : 0, e_out1 = bus_on ? (int)t_oute[sl] : 0;
+  const int j0 = bus_on ? (int)t_genb[sl] : 0, j1 = bus_on ? (int)t_gene[sl] : 0;
+  const int deg = e_in1 - e_in0;                        // lines walked by this slot
+  const float degf = (float)(e_full1 - e_in0);          // in-degree of the bus (primary)
   const bool is_gen = j1 > j0;
   const int warp_max_deg = __reduce_max_sync(0xffffffffu, deg);
 
@@ -183,10 +197,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
     load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
     __syncthreads();
     float part4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (bus_on) {
-      part4[0] = s_busc[0 * NG + nb];
-      const float r = s_linef[0 * EG + nb], x = s_linef[1 * EG + nb];     // line id == slot here
-      s_y[nb] = 1.0f / sqrtf(r * r + x * x);
+    if (bus_on) part4[0] = s_busc[0 * NG + nb];
+    if (slot < N) {                                                        // `slot` is an alias LINE id here
+      const float r = s_linef[0 * EG + jb], x = s_linef[1 * EG + jb];
+      s_y[jb] = 1.0f / sqrtf(r * r + x * x);
     }
     for (int it = tid; it < Gn * NGQ; it += T) {
       part4[1] += s_genc[2 * GnG + it];
@@ -259,11 +273,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         part[0] = gdP * cs;
         vprime = s_nxt[0 * NG + nb];
         Gs = s_busc[2 * NG + nb];
-        // alias line j == slot: D_j = theta'[f_j] - theta'[t_j]
-        const float d = s_nxt[1 * NG + (int)t_fi[n] * G + gq] - s_nxt[1 * NG + (int)t_ti[n] * G + gq];
+      }
+      if (slot < N) {   // alias line j == slot: D_j = theta'[f_j] - theta'[t_j]
+        const float d = s_nxt[1 * NG + (int)t_fi[slot] * G + gq] - s_nxt[1 * NG + (int)t_ti[slot] * G + gq];
         float sd, cd;
         fast_sincos(d, sd, cd);
-        s_trig[0 * NG + nb] = d; s_trig[1 * NG + nb] = sd; s_trig[2 * NG + nb] = cd;
+        s_trig[0 * NG + jb] = d; s_trig[1 * NG + jb] = sd; s_trig[2 * NG + jb] = cd;
       }
       block_sum_per_grid<1>(part, s_red, NGQ);      // its barriers also publish s_w, s_state, s_trig, gdP
       const float adj_pg = part[0] / (lo_branch ? 2.f * (sPset - sPmin) : 2.f * (sPmax - sPset));
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           const int eo = (int)t_outi[e] * G + gq;
           sv += s_lineg[0 * EG + eo]; sth += s_lineg[2 * EG + eo]; sD += s_lineg[3 * EG + eo];
         }
-        for (int e = e_in0; e < e_in1; ++e) {
+        for (int e = e_in0; e < e_full1; ++e) {
           const int eo = (int)t_ini[e] * G + gq;
           sv += s_lineg[1 * EG + eo]; sth -= s_lineg[2 * EG + eo]; sD += s_lineg[4 * EG + eo];
         }
@@ -329,7 +344,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       __syncthreads();
       if (bus_on) {                                        // D_e = theta[f_e] - theta[t_e] for alias lines e < N
         for (int e = e_out0; e < e_out1; ++e) { const int l = t_outi[e]; if (l < N) adjth += s_adjD[l * G + gq]; }
-        for (int e = e_in0; e < e_in1; ++e) { const int l = t_ini[e]; if (l < N) adjth -= s_adjD[l * G + gq]; }
+        for (int e = e_in0; e < e_full1; ++e) { const int l = t_ini[e]; if (l < N) adjth -= s_adjD[l * G + gq]; }
       }
       // adjv / adjth now hold d loss / d v', d theta' of this thread's bus (registers).
 
@@ -387,6 +402,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
             for (int o = 0; o < H; ++o) A[o] += lrelu(z2[o][0]);
           }
+          if (warp_has_twins) {   // combine the partial aggregates of a bus split over twin lanes
+#pragma unroll
+            for (int d = 1; d < 4; d *= 2) {
+#pragma unroll
+              for (int o = 0; o < H; ++o) {
+                const float t = __shfl_xor_sync(0xffffffffu, A[o], d * NGQ);
+                if (gsz > d) A[o] += t;
+              }
+            }
+          }
         };
 
         // adjoint of one phi net given adjA: line loop, dW2 / db2 / dW1f, adjP, dW1m / db1, adj m
@@ -394,8 +419,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           float adjP[H];
 #pragma unroll
           for (int o = 0; o < H; ++o) adjP[o] = 0.f;
+          if (warp_has_twins) {   // twins take the aggregate's adjoint from the bus owner
+#pragma unroll
+            for (int o = 0; o < H; ++o) adjA[o] = __shfl_sync(0xffffffffu, adjA[o], leader_lane);
+          }
           for (int it = 0; it < warp_max_deg; ++it) {
-            const bool live = bus_on && (it < deg);
+            const bool live = slot_on && (it < deg);
             const float* wp = wphi + opaque_zero();
             float z[H][1], z2[H][1], d2[H], d1[H], feat[5];
             const float* lf = s_linef + (int)t_ini[live ? e_in0 + it : 0] * G + gq;
@@ -446,6 +475,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             // dW1f^T[c5][o] += feat[c5] d1[o]
             tile_gemm<H>(5, [&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi,
                          [&](int r, int c) { return W.phi_w1f + r * HP + c; });
+          }
+          if (warp_has_twins) {   // the bus owner needs the sum over its twins
+#pragma unroll
+            for (int d = 1; d < 4; d *= 2) {
+#pragma unroll
+              for (int o = 0; o < H; ++o) {
+                const float t = __shfl_xor_sync(0xffffffffu, adjP[o], d * NGQ);
+                if (gsz > d) adjP[o] += t;
+              }
+            }
           }
           __syncwarp();
 #pragma unroll

@@ -84,30 +84,44 @@ __host__ __device__ constexpr WLayout make_wlayout(int L, int H, bool multi) {
 // All entries are uint16 (n_bus, n_line < 65536).
 // ---------------------------------------------------------------------------------
 struct TopoOffsets {      // offsets in uint16 units inside the index block
-  int fi, ti;             // [E] internal slot of from / to bus
+  // Internal index space = SLOTS.  Every bus owns one primary slot; a bus with more than
+  // `cap` incoming lines owns 2 or 4 adjacent slots ("twins") that split its in-lines, so
+  // no lane walks more than ~cap lines.  Ns = number of slots >= N.
+  int fi, ti;             // [E] primary slot of from / to bus
   int fa, ta;             // [E] alias line ids: external from / to bus number re-read as a line id
-  int in_ptr, in_ids;     // [N+1], [E] lines entering internal slot n (ascending line id)
-  int out_ptr, out_ids;   // [N+1], [E] lines leaving internal slot n
-  int gen_ptr, gen_ids;   // [N+1], [Gn] generators sitting on internal slot n
-  int ext_of;             // [N] external bus of internal slot
-  int rank_of;            // [N] internal slot of external bus
+  int in_b, in_e, in_fe;  // [Ns] in-line range walked by this slot; end of the bus's full range (primary)
+  int in_ids;             // [E] line ids grouped by receiving bus (ascending line id inside a bus)
+  int out_b, out_e;       // [Ns] out-line range (primary slots only, else empty)
+  int out_ids;            // [E]
+  int gen_b, gen_e;       // [Ns] generator range (primary slots only)
+  int gen_ids;            // [Gn]
+  int ext_of;             // [Ns] external bus of the slot
+  int prim_of;            // [Ns] primary slot of the slot's bus
+  int gsz;                // [Ns] slots in this bus's twin group (1, 2 or 4), aligned to gsz
+  int rank_of;            // [N]  primary slot of external bus
   int total;              // padded to a multiple of 8
 };
 
-__host__ __device__ inline TopoOffsets make_topo_offsets(int N, int E, int Gn) {
+__host__ __device__ inline TopoOffsets make_topo_offsets(int N, int Ns, int E, int Gn) {
   TopoOffsets t{};
   int o = 0;
   t.fi = o; o += E;
   t.ti = o; o += E;
   t.fa = o; o += E;
   t.ta = o; o += E;
-  t.in_ptr = o; o += N + 1;
+  t.in_b = o; o += Ns;
+  t.in_e = o; o += Ns;
+  t.in_fe = o; o += Ns;
   t.in_ids = o; o += E;
-  t.out_ptr = o; o += N + 1;
+  t.out_b = o; o += Ns;
+  t.out_e = o; o += Ns;
   t.out_ids = o; o += E;
-  t.gen_ptr = o; o += N + 1;
+  t.gen_b = o; o += Ns;
+  t.gen_e = o; o += Ns;
   t.gen_ids = o; o += Gn;
-  t.ext_of = o; o += N;
+  t.ext_of = o; o += Ns;
+  t.prim_of = o; o += Ns;
+  t.gsz = o; o += Ns;
   t.rank_of = o; o += N;
   t.total = (o + 7) & ~7;
   return t;
@@ -285,8 +299,8 @@ struct FwdArgs {
   float* pglob;            // [nbatch][K][G] or null
   const uint16_t* topo;    // index block in global memory
   long long S;
-  int N, E, Gn, K, NGQ, G, nbatch;
-  int NGs, EGs;            // padded row strides of the [.][N][G] and [.][E][G] arrays
+  int N, Ns, E, Gn, K, NGQ, G, nbatch;   // Ns = bus slots (>= N)
+  int NGs, EGs;            // padded row strides of the [.][Ns][G] and [.][E][G] arrays
   int need_grad;
   unsigned char grp_of_warp[32];   // warp -> group of 32/NGQ consecutive bus slots
   SmemPlan sm;

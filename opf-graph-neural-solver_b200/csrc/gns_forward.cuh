@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const int slot = (int)a.grp_of_warp[tid >> 5] * (32 / NGQ) + (tid & 31) / NGQ;
   const int gq = (tid & 31) % NGQ;
   const int gcol = gq * VG;
-  const bool bus_on = slot < N;
+  const bool slot_on = slot < a.Ns;     // this thread owns a bus slot (primary or twin)
 
   // topology indices: once per CTA
   for (int i = tid; i < a.to.total / 2; i += T)
@@ -50,15 +50,32 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const uint16_t* const t_ti = s_topo + a.to.ti;
   const uint16_t* const t_fa = s_topo + a.to.fa;
   const uint16_t* const t_ta = s_topo + a.to.ta;
-  const uint16_t* const t_inp = s_topo + a.to.in_ptr;
+  const uint16_t* const t_inb = s_topo + a.to.in_b;
+  const uint16_t* const t_ine = s_topo + a.to.in_e;
+  const uint16_t* const t_infe = s_topo + a.to.in_fe;
   const uint16_t* const t_ini = s_topo + a.to.in_ids;
-  const uint16_t* const t_outp = s_topo + a.to.out_ptr;
+  const uint16_t* const t_outb = s_topo + a.to.out_b;
+  const uint16_t* const t_oute = s_topo + a.to.out_e;
   const uint16_t* const t_outi = s_topo + a.to.out_ids;
-  const uint16_t* const t_genp = s_topo + a.to.gen_ptr;
+  const uint16_t* const t_genb = s_topo + a.to.gen_b;
+  const uint16_t* const t_gene = s_topo + a.to.gen_e;
   const uint16_t* const t_geni = s_topo + a.to.gen_ids;
   const uint16_t* const t_ext = s_topo + a.to.ext_of;
   const uint16_t* const t_rank = s_topo + a.to.rank_of;
+  const uint16_t* const t_prim = s_topo + a.to.prim_of;
+  const uint16_t* const t_gsz = s_topo + a.to.gsz;
   __syncthreads();
+  // slot bookkeeping (constant over batches)
+  const int sl = slot_on ? slot : 0;
+  const int pslot = t_prim[sl];                       // primary slot of this slot's bus: owns the state
+  const bool prim = slot_on && pslot == sl;           // this thread owns the bus (twins only help with lines)
+  const bool bus_on = prim;
+  const int gsz = slot_on ? (int)t_gsz[sl] : 1;       // twin group size (1, 2, 4), group aligned to gsz
+  const bool warp_has_twins = __any_sync(0xffffffffu, gsz > 1);
+  const int e_in0 = slot_on ? (int)t_inb[sl] : 0, e_in1 = slot_on ? (int)t_ine[sl] : 0;   // lines this slot walks
+  const int e_full1 = prim ? (int)t_infe[sl] : e_in0;                                       // end of the bus's in-list
+  const int e_out0 = prim ? (int)t_outb[sl] : 0, e_out1 = prim ? (int)t_oute[sl] : 0;
+  const int j0 = prim ? (int)t_genb[sl] : 0, j1 = prim ? (int)t_gene[sl] : 0;
 
   for (int batch = blockIdx.x; batch < a.nbatch; batch += gridDim.x) {
     const long long g0 = (long long)batch * G;
@@ -70,7 +87,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     __syncthreads();
 
     // ---------------- state init (ref GNS/main.py:141-152) ----------------
-    int e_in0 = 0, e_in1 = 0, e_out0 = 0, e_out1 = 0, j0 = 0, j1 = 0;
     float part4[4][VG];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -78,9 +94,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       for (int g = 0; g < VG; ++g) part4[q][g] = 0.f;
     if (bus_on) {
       const int n = slot;
-      e_in0 = t_inp[n]; e_in1 = t_inp[n + 1];
-      e_out0 = t_outp[n]; e_out1 = t_outp[n + 1];
-      j0 = t_genp[n]; j1 = t_genp[n + 1];
       float vv[VG], pg[VG], qg[VG];
 #pragma unroll
       for (int g = 0; g < VG; ++g) { vv[g] = 0.f; pg[g] = 0.f; qg[g] = 0.f; }
@@ -120,13 +133,14 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       for (int i = 0; i < L; ++i) IO::st(st + (4 + i) * NG, o);
 #pragma unroll
       for (int g = 0; g < VG; ++g) part4[0][g] = Pd[g];
-      // alias-line admittance magnitude, lines 0..N-1 (ref GNS/main.py:38,87)
+    }
+    if (slot < N) {   // alias-line admittance magnitude, lines 0..N-1 (ref GNS/main.py:38,87); slot = LINE id here
       float r[VG], x[VG], y[VG];
-      IO::ld(r, s_linef + 0 * EG + n * G + gcol);
-      IO::ld(x, s_linef + 1 * EG + n * G + gcol);
+      IO::ld(r, s_linef + 0 * EG + slot * G + gcol);
+      IO::ld(x, s_linef + 1 * EG + slot * G + gcol);
 #pragma unroll
       for (int g = 0; g < VG; ++g) y[g] = 1.0f / sqrtf(r[g] * r[g] + x[g] * x[g]);
-      IO::st(s_y + n * G + gcol, y);
+      IO::st(s_y + slot * G + gcol, y);
     }
     for (int it = tid; it < Gn * NGQ; it += T) {
       const int j = it / NGQ;
@@ -172,11 +186,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       __syncthreads();
 
       // ---------------- bus phase: phi nets, aggregation, L nets ----------------
-      if (bus_on) {
-        const int n = slot;
+      {
+        const int n = pslot;                         // the bus's state lives in its primary slot
         float* st = s_state + n * G + gcol;
         const float* sm_m = st + 4 * NG;
-        const float degf = (float)(e_in1 - e_in0);
+        const float degf = (float)(e_full1 - e_in0); // in-degree of the bus (primary)
         float st4[4][VG];
 #pragma unroll
         for (int q = 0; q < 4; ++q) IO::ld(st4[q], st + q * NG);
@@ -185,6 +199,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
           if (MULTI || q == 0) {
+#pragma unroll
+            for (int o = 0; o < H; ++o)
+#pragma unroll
+              for (int g = 0; g < VG; ++g) A[o][g] = 0.f;
+           if (slot_on) {
             const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
             float P[H][VG];
             {
@@ -201,10 +220,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
               IO::ld(x, sm_m + i * NG);
               row_axpy<H, HP, VG>(P, x, wphi + W.phi_w1m + i * HP);
             }
-#pragma unroll
-            for (int o = 0; o < H; ++o)
-#pragma unroll
-              for (int g = 0; g < VG; ++g) A[o][g] = 0.f;
             for (int e = e_in0; e < e_in1; ++e) {
               const float* lf = s_linef + (int)t_ini[e] * G + gcol;
               wphi += opaque_zero();   // keep the weight rows in shared memory (no LICM into spills)
@@ -235,7 +250,21 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
                 for (int g = 0; g < VG; ++g) A[o][g] += lrelu(z2[o][g]);
             }
+           }
+            if (warp_has_twins) {   // twins: combine the partial aggregates of a bus (lanes NGQ apart)
+#pragma unroll
+              for (int d = 1; d < 4; d *= 2) {
+#pragma unroll
+                for (int o = 0; o < H; ++o)
+#pragma unroll
+                  for (int g = 0; g < VG; ++g) {
+                    const float t = __shfl_xor_sync(0xffffffffu, A[o][g], d * NGQ);
+                    if (gsz > d) A[o][g] += t;
+                  }
+              }
+            }
           }
+          if (!prim) continue;
           const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
           float zL[H][VG];
@@ -308,19 +337,21 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
           }
         }
         // state update (ref GNS/main.py:182-188); v only moves on non-generator buses
-        const bool is_gen = j1 > j0;
+        if (prim) {
+          const bool is_gen = j1 > j0;
 #pragma unroll
-        for (int g = 0; g < VG; ++g) {
-          st4[1][g] = st4[1][g] + dth[g];
-          if (!is_gen) st4[0][g] = st4[0][g] + dv[g];
+          for (int g = 0; g < VG; ++g) {
+            st4[1][g] = st4[1][g] + dth[g];
+            if (!is_gen) st4[0][g] = st4[0][g] + dv[g];
+          }
+          IO::st(st + 0 * NG, st4[0]);
+          IO::st(st + 1 * NG, st4[1]);
         }
-        IO::st(st + 0 * NG, st4[0]);
-        IO::st(st + 1 * NG, st4[1]);
       }
       __syncthreads();
 
       // ---------------- physics 1: angle difference of the alias lines 0..N-1 ----------------
-      if (bus_on) {
+      if (slot < N) {
         const int j = slot;  // used as a LINE id here
         float tf[VG], tt[VG], d[VG], sd[VG], cd[VG];
         IO::ld(tf, s_state + 1 * NG + (int)t_fi[j] * G + gcol);
@@ -430,7 +461,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         float spf[VG], sqf[VG], spt[VG], sqt[VG];
 #pragma unroll
         for (int g = 0; g < VG; ++g) { spf[g] = 0.f; sqf[g] = 0.f; spt[g] = 0.f; sqt[g] = 0.f; }
-        for (int e = e_in0; e < e_in1; ++e) {
+        for (int e = e_in0; e < e_full1; ++e) {
           const int line = t_ini[e];
           float x[VG];
           IO::ld(x, s_flow + 0 * EG + line * G + gcol);

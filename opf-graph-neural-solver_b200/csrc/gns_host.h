@@ -13,12 +13,15 @@
 struct gns_plan {
   int device = 0;
   int N = 0, E = 0, Gn = 0;
+  int Ns = 0;                       // bus slots (high-degree buses own 2 or 4)
+  int deg_cap = 2, max_gsz = 1;
   int num_sms = 0;
   int smem_optin = 0;
   // host copies (int32) for export and tests
   std::vector<int32_t> f_bus, t_bus, gen_bus;
   std::vector<int32_t> in_rowptr, in_lines, out_rowptr, out_lines, gen_rowptr, gen_ids;
   std::vector<int32_t> bus_order, bus_rank;
+  std::vector<int32_t> slot_bus, slot_primary, slot_in_begin, slot_in_end, slot_gsz;   // slot tables
   // device index block (uint16) + float copies of the expected index columns
   gns::TopoOffsets to{};
   uint16_t* d_topo = nullptr;

@@ -42,8 +42,8 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? std::atoi(s) : dflt;
 }
 
-static SmemPlan plan_smem(int N, int E, int Gn, int G, int L, int wstep, int nwarps, int topo_u16,
-                          int extra_floats) {
+static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, int wstep, int nwarps, int topo_u16,
+                          int extra_floats, bool backward) {
   SmemPlan s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
@@ -54,7 +54,7 @@ static SmemPlan plan_smem(int N, int E, int Gn, int G, int L, int wstep, int nwa
   s.linef = take(5 * EGs);
   s.yline = take(NGs);
   s.trig = take(3 * NGs);
-  s.flows = take(4 * EGs);
+  s.flows = take(backward ? 0 : 4 * EGs);   // the backward kernel keeps its own per-line block
   s.gsum = take(4 * G);
   s.red = take(nwarps * G);
   s.weights = take(wstep);
@@ -76,10 +76,8 @@ static void balance_warps(const gns_plan* plan, Geometry* g) {
   std::vector<std::pair<float, int>> cost(nw);
   for (int grp = 0; grp < nw; ++grp) {
     int mx = -1;
-    for (int s = grp * spw; s < std::min((grp + 1) * spw, plan->N); ++s) {
-      const int b = plan->bus_order[s];
-      mx = std::max(mx, plan->in_rowptr[b + 1] - plan->in_rowptr[b]);
-    }
+    for (int s = grp * spw; s < std::min((grp + 1) * spw, plan->Ns); ++s)
+      mx = std::max(mx, plan->slot_in_end[s] - plan->slot_in_begin[s]);
     cost[grp] = {mx < 0 ? 0.f : 1.f + 0.15f * mx, grp};
   }
   std::stable_sort(cost.begin(), cost.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
@@ -101,7 +99,7 @@ static void balance_warps(const gns_plan* plan, Geometry* g) {
 }
 
 bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, bool backward, Geometry* out) {
-  const int N = plan->N, E = plan->E, Gn = plan->Gn;
+  const int N = plan->Ns, E = plan->E, Gn = plan->Gn;   // N = bus slots here
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
   const int limit = plan->smem_optin;
   Geometry best{};
@@ -118,6 +116,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       if (force_ngq && NGQ != force_ngq) continue;
       const int T = ((N * NGQ + 31) / 32) * 32;
       if (T > 1024) continue;
+      if (32 / NGQ < plan->max_gsz) continue;     // a twin group must stay inside one warp
       const int G = VG * NGQ;
       const long long nb = (S + G - 1) / G;
       if (!force_ngq && NGQ > 1 && (T > std::max(target_threads, 32) || nb < 2LL * plan->num_sms)) continue;
@@ -126,7 +125,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       g.tmax = (T <= 384) ? 384 : 1024;
       if (g.tmax == 1024 && VG != 1) continue;   // the wide-CTA variant exists for VG=1 only
       const int extra = backward ? backward_extra_floats(N, E, G, md.L, md.H, T) : 0;
-      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra);
+      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward);
       const size_t bytes = (size_t)sm.total_floats * 4;
       if ((int)bytes > limit) continue;
       g.smem_bytes = bytes; g.sm = sm;
@@ -225,7 +224,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
   size_t o = 0;
   w.packed_params = o; o = align(o + (size_t)md.K * W.wstep * 4);
   if (need_grad) {
-    const size_t nst = (size_t)(4 + md.L) * row_stride(plan->N * fwd.G);
+    const size_t nst = (size_t)(4 + md.L) * row_stride(plan->Ns * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * W.wstep * 4);   // one block per warp
@@ -280,31 +279,77 @@ extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* 
   p->bus_rank.resize(n_bus);
   for (int s = 0; s < n_bus; ++s) p->bus_rank[p->bus_order[s]] = s;
 
-  // device index block in INTERNAL slot numbering
-  p->to = make_topo_offsets(n_bus, n_line, n_gen);
+  // ---- slots: a bus with more than deg_cap incoming lines is split over 2 or 4 adjacent slots ----
+  p->deg_cap = std::max(1, env_int("GNS_DEG_CAP", 2));
+  const int max_group = std::max(1, std::min(4, env_int("GNS_MAX_TWINS", 4)));
+  auto group_size = [&](int deg) {
+    int need = (deg + p->deg_cap - 1) / p->deg_cap, g = 1;
+    while (g < need && g < max_group) g *= 2;
+    return g;
+  };
+  // bus_order is degree-descending, so group sizes are non-increasing along it and every group
+  // starts at a multiple of its own size: twin groups never straddle a warp's slot range.
+  p->slot_bus.clear(); p->slot_primary.clear(); p->slot_in_begin.clear(); p->slot_in_end.clear(); p->slot_gsz.clear();
+  std::vector<int32_t> prim_slot_of_bus(n_bus, 0);
+  {
+    int in_off = 0;
+    for (int s0 = 0; s0 < n_bus; ++s0) {
+      const int b = p->bus_order[s0];
+      const int deg = p->in_rowptr[b + 1] - p->in_rowptr[b];
+      const int g = group_size(deg);
+      p->max_gsz = std::max(p->max_gsz, g);
+      const int chunk = (deg + g - 1) / g;
+      const int first = (int)p->slot_bus.size();
+      prim_slot_of_bus[b] = first;
+      for (int i = 0; i < g; ++i) {
+        const int lo = std::min(deg, i * chunk), hi = std::min(deg, (i + 1) * chunk);
+        p->slot_bus.push_back(b);
+        p->slot_primary.push_back(first);
+        p->slot_in_begin.push_back(in_off + lo);
+        p->slot_in_end.push_back(in_off + hi);
+        p->slot_gsz.push_back(g);
+      }
+      in_off += deg;
+    }
+  }
+  p->Ns = (int)p->slot_bus.size();
+  const int Ns = p->Ns;
+  if (Ns > 65535) { set_error("gns_plan_create: too many bus slots"); delete p; return -1; }
+
+  // device index block in slot numbering
+  p->to = make_topo_offsets(n_bus, Ns, n_line, n_gen);
   std::vector<uint16_t> blk(p->to.total, 0);
   for (int e = 0; e < n_line; ++e) {
-    blk[p->to.fi + e] = (uint16_t)p->bus_rank[f_bus[e]];
-    blk[p->to.ti + e] = (uint16_t)p->bus_rank[t_bus[e]];
+    blk[p->to.fi + e] = (uint16_t)prim_slot_of_bus[f_bus[e]];
+    blk[p->to.ti + e] = (uint16_t)prim_slot_of_bus[t_bus[e]];
     blk[p->to.fa + e] = (uint16_t)f_bus[e];
     blk[p->to.ta + e] = (uint16_t)t_bus[e];
   }
   {
     int oi = 0, oo = 0, og = 0;
-    for (int s = 0; s < n_bus; ++s) {
-      const int b = p->bus_order[s];
-      blk[p->to.in_ptr + s] = (uint16_t)oi;
+    for (int s0 = 0; s0 < n_bus; ++s0) {       // id lists in primary-slot order
+      const int b = p->bus_order[s0];
+      const int ps = prim_slot_of_bus[b];
+      const int in0 = oi;
       for (int q = p->in_rowptr[b]; q < p->in_rowptr[b + 1]; ++q) blk[p->to.in_ids + oi++] = (uint16_t)p->in_lines[q];
-      blk[p->to.out_ptr + s] = (uint16_t)oo;
+      for (int s = ps; s < ps + p->slot_gsz[ps]; ++s) blk[p->to.in_fe + s] = (uint16_t)oi;
+      (void)in0;
+      blk[p->to.out_b + ps] = (uint16_t)oo;
       for (int q = p->out_rowptr[b]; q < p->out_rowptr[b + 1]; ++q) blk[p->to.out_ids + oo++] = (uint16_t)p->out_lines[q];
-      blk[p->to.gen_ptr + s] = (uint16_t)og;
+      blk[p->to.out_e + ps] = (uint16_t)oo;
+      blk[p->to.gen_b + ps] = (uint16_t)og;
       for (int q = p->gen_rowptr[b]; q < p->gen_rowptr[b + 1]; ++q) blk[p->to.gen_ids + og++] = (uint16_t)p->gen_ids[q];
-      blk[p->to.ext_of + s] = (uint16_t)b;
-      blk[p->to.rank_of + b] = (uint16_t)s;
+      blk[p->to.gen_e + ps] = (uint16_t)og;
+      blk[p->to.rank_of + b] = (uint16_t)ps;
     }
-    blk[p->to.in_ptr + n_bus] = (uint16_t)oi;
-    blk[p->to.out_ptr + n_bus] = (uint16_t)oo;
-    blk[p->to.gen_ptr + n_bus] = (uint16_t)og;
+    for (int s = 0; s < Ns; ++s) {
+      blk[p->to.in_b + s] = (uint16_t)p->slot_in_begin[s];
+      blk[p->to.in_e + s] = (uint16_t)p->slot_in_end[s];
+      blk[p->to.ext_of + s] = (uint16_t)p->slot_bus[s];
+      blk[p->to.prim_of + s] = (uint16_t)p->slot_primary[s];
+      blk[p->to.gsz + s] = (uint16_t)p->slot_gsz[s];
+      // non-primary slots keep empty out / generator ranges (zero-initialised begin == end)
+    }
   }
   std::vector<float> expect(2 * n_line + n_gen);
   for (int e = 0; e < n_line; ++e) { expect[e] = (float)(f_bus[e] + 1); expect[n_line + e] = (float)(t_bus[e] + 1); }
@@ -354,6 +399,11 @@ extern "C" int gns_plan_export(const gns_plan* p, const char* name, int32_t* out
   else if (s == "gen_ids") v = &p->gen_ids;
   else if (s == "bus_order") v = &p->bus_order;
   else if (s == "bus_rank") v = &p->bus_rank;
+  else if (s == "slot_bus") v = &p->slot_bus;
+  else if (s == "slot_primary") v = &p->slot_primary;
+  else if (s == "slot_in_begin") v = &p->slot_in_begin;
+  else if (s == "slot_in_end") v = &p->slot_in_end;
+  else if (s == "slot_gsz") v = &p->slot_gsz;
   else { set_error("gns_plan_export: unknown array '" + s + "'"); return -1; }
   if (out) {
     if (capacity < (int)v->size()) { set_error("gns_plan_export: capacity too small"); return -1; }

@@ -153,3 +153,29 @@ def test_forward_without_cuda_fails_loudly():
 def test_block_forward_is_not_a_side_door():
     with pytest.raises(RuntimeError):
         pkg.LearningBlock(3, 4, 5)(torch.zeros(1, 3))
+
+
+@pytest.mark.parametrize("n_bus", [14, 30, 118, 300])
+def test_slot_tables_split_high_degree_buses_consistently(lib, n_bus):
+    """Every bus owns 1, 2 or 4 adjacent, aligned slots whose line ranges tile its in-list."""
+    case, _ = pkg.data.get_case(n_bus)
+    f = case["branch"][:, 0].astype(np.int32) - 1
+    t = case["branch"][:, 1].astype(np.int32) - 1
+    gb = case["gen"][:, 0].astype(np.int32) - 1
+    plan = _host_plan(f, t, gb, n_bus)
+    sb, sp, b0, b1, gs = (plan.export(k) for k in ("slot_bus", "slot_primary", "slot_in_begin", "slot_in_end", "slot_gsz"))
+    order = plan.export("bus_order")
+    deg = np.diff(plan.export("in_rowptr"))
+    assert np.array_equal(sb[sp == np.arange(len(sb))], order)           # primaries appear in bus order
+    pos = 0
+    covered = 0
+    for b in order:
+        g = gs[pos]
+        assert g in (1, 2, 4) and pos % g == 0                           # aligned twin group
+        assert (sb[pos:pos + g] == b).all() and (sp[pos:pos + g] == pos).all() and (gs[pos:pos + g] == g).all()
+        assert b0[pos] == covered and b1[pos + g - 1] == covered + deg[b]
+        assert (b0[pos + 1:pos + g] == b1[pos:pos + g - 1]).all()        # consecutive sub-ranges
+        assert (b1[pos:pos + g] - b0[pos:pos + g]).max() <= max(2, -(-deg[b] // 4))
+        covered += deg[b]
+        pos += g
+    assert pos == len(sb) and covered == len(t)
