@@ -17,7 +17,7 @@ SYMBOLS = [
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libgns_b200.so")
+    return os.environ.get("GNS_LIB") or os.path.join(_HERE, "libgns_b200.so")
 
 
 def build_library(verbose: bool = False) -> str:
