@@ -19,6 +19,15 @@
 
 namespace gns {
 
+#ifndef GNS_BWD_L2PREFETCH
+#define GNS_BWD_L2PREFETCH 1
+#endif
+#ifndef GNS_TG_SPLIT
+#define GNS_TG_SPLIT 1
+#endif
+#ifndef GNS_TG_PREFETCH
+#define GNS_TG_PREFETCH 1
+#endif
 constexpr int kTS = 36;   // tile row stride in floats: 32 items + 4 (odd number of 16 B groups)
 
 struct BwdSmem {          // offsets in floats from SmemPlan.extra
@@ -66,32 +75,69 @@ struct BwdArgs {
   float wk[kMaxK];
 };
 
-// dW^T[r][c] += sum_{item<32} row_r[item] * hid_c[item] for the lane-owned rows r = lane, lane+32, ...
+// dW^T[r][c] += sum_{item<32} row_r[item] * hid_c[item]   for rows r in [rb, re).
 // rowfn(r) -> pointer to 32 consecutive floats (16-byte aligned); hid rows are kTS apart;
 // outfn(r, c) -> offset inside this warp's private accumulator block.
-template <int C, class RowFn, class OutFn>
-__device__ __forceinline__ void tile_gemm(int R, RowFn rowfn, const float* __restrict__ hid, float* __restrict__ g,
-                                          OutFn outfn) {
+// PARTS lanes share one row, each running over 32/PARTS items, and are folded by shuffles: a
+// chunk of <= 8 (<= 16) rows keeps 32 lanes busy with 4 (2) item parts instead of idling 24 (16).
+template <int C, int PARTS, class RowFn, class OutFn>
+__device__ __forceinline__ void tile_gemm_chunk(int rb, int re, RowFn rowfn, const float* __restrict__ hid,
+                                                float* __restrict__ g, OutFn outfn) {
+  constexpr int RW = 32 / PARTS;          // rows per pass
+  constexpr int QP = 8 / PARTS;           // item quads per part
   const int lane = threadIdx.x & 31;
-  for (int r = lane; r < R; r += 32) {
-    const float4* a4 = reinterpret_cast<const float4*>(rowfn(r));
+  const int part = lane / RW;
+  for (int r0 = rb; r0 < re; r0 += RW) {
+    const int r = r0 + (lane % RW);
+    const bool on = r < re;
+    const float4* a4 = reinterpret_cast<const float4*>(rowfn(on ? r : rb)) + part * QP;
+    const float* h0 = hid + 4 * part * QP;
+    const bool writer = on && part == 0;
     float acc[C];
+#if GNS_TG_PREFETCH
+    float old[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) old[c] = writer ? g[outfn(r, c)] : 0.f;
+#endif
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
 #pragma unroll 2
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < QP; ++q) {
       const float4 av = a4[q];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float4 h = *reinterpret_cast<const float4*>(hid + c * kTS + 4 * q);
+        const float4 h = *reinterpret_cast<const float4*>(h0 + c * kTS + 4 * q);
         acc[c] = fmaf(av.x, h.x, fmaf(av.y, h.y, fmaf(av.z, h.z, fmaf(av.w, h.w, acc[c]))));
       }
     }
+    if (PARTS > 1) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float* p = g + outfn(r, c);
-      *p += acc[c];
+      for (int d = RW; d < 32; d *= 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+      }
     }
+    if (writer) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#if GNS_TG_PREFETCH
+        g[outfn(r, c)] = old[c] + acc[c];
+#else
+        float* p = g + outfn(r, c);
+        *p += acc[c];
+#endif
+      }
+    }
+  }
+}
+
+template <int C, int R, class RowFn, class OutFn>
+__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hid, float* __restrict__ g, OutFn outfn) {
+  constexpr int FULL = (R / 32) * 32, REM = R - FULL;
+  if (FULL > 0) tile_gemm_chunk<C, 1>(0, FULL, rowfn, hid, g, outfn);
+  if (REM > 0) {
+    constexpr int P = GNS_TG_SPLIT ? (REM <= 8 ? 4 : (REM <= 16 ? 2 : 1)) : 1;
+    tile_gemm_chunk<C, P>(FULL, R, rowfn, hid, g, outfn);
   }
 }
 
@@ -225,6 +271,13 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 
     for (int k = K - 1; k >= 0; --k) {
       // ---------------- stage weights and state_k ----------------
+#if GNS_BWD_L2PREFETCH
+      {   // pull this warp's step-k accumulator block towards L2 now; the read-modify-writes of the
+          // weight-gradient tiles then see L2 latency instead of DRAM latency
+        const char* blk = reinterpret_cast<const char*>(gacc_w + (size_t)k * W.wstep);
+        for (int i = lane * 128; i < W.wstep * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
+      }
+#endif
       {
         const float4* src = reinterpret_cast<const float4*>(a.params + (size_t)k * W.wstep);
         float4* dst = reinterpret_cast<float4*>(s_w);
@@ -468,12 +521,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             for (int c = 0; c < 5; ++c) tile[(R_WIDE + H + 1 + c) * kTS + lane] = live ? feat[c] : 0.f;
             __syncwarp();
             // dW2^T[j][o] += h1[j] d2[o];  db2[o] += d2[o]
-            tile_gemm<H>(H + 1,
-                         [&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
+            tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
                          tile + R_HID * kTS, gphi,
                          [&](int r, int c) { return (r < H ? W.phi_w2 + r * HP : W.phi_b2) + c; });
             // dW1f^T[c5][o] += feat[c5] d1[o]
-            tile_gemm<H>(5, [&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi,
+            tile_gemm_r<H, 5>([&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi,
                          [&](int r, int c) { return W.phi_w1f + r * HP + c; });
           }
           if (warp_has_twins) {   // the bus owner needs the sum over its twins
@@ -491,8 +543,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int o = 0; o < H; ++o) stage(R_HID + o, adjP[o]);
           __syncwarp();
           // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
-          tile_gemm<H>(L + 1,
-                       [&](int r) { return r < L ? rows_state + (4 + r) * NG : tile + R_ONES * kTS; },
+          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_state + (4 + r) * NG : tile + R_ONES * kTS; },
                        tile + R_HID * kTS, gphi,
                        [&](int r, int c) { return (r < L ? W.phi_w1m + r * HP : W.phi_b1) + c; });
           {
@@ -563,8 +614,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             stage(R_HID, g);
             __syncwarp();
             // dWout[j] += g h2[j];  dbout += g      (rows = [h2 (H), ones], one column g)
-            tile_gemm<1>(H + 1,
-                         [&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
+            tile_gemm_r<1, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
                          tile + R_HID * kTS, gln,
                          [&](int r, int) { return r < H ? W.ln_wo + r : W.ln_bo_s; });
           } else {
@@ -578,7 +628,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             stage(R_HID + H, 1.f);
             __syncwarp();
             // dWout[i][j] += adjm'[i] h2[j];  dbout[i] += adjm'[i]    (rows = adj m' rows in place)
-            tile_gemm<H + 1>(L, [&](int r) { return rows_adj + (4 + r) * NG; }, tile + R_HID * kTS, gln,
+            tile_gemm_r<H + 1, L>([&](int r) { return rows_adj + (4 + r) * NG; }, tile + R_HID * kTS, gln,
                              [&](int r, int c) { return c < H ? W.ln_wo + r * HP + c : W.ln_bo_m + r; });
           }
           __syncwarp();
@@ -591,8 +641,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             stage(R_WIDE + o, h1L[o][0]);
           }
           __syncwarp();
-          tile_gemm<H>(H + 1,
-                       [&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
+          tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
                        tile + R_HID * kTS, gln,
                        [&](int r, int c) { return (r < H ? W.ln_w2 + r * HP : W.ln_b2) + c; });
 #pragma unroll
@@ -606,8 +655,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
           for (int o = 0; o < H; ++o) stage(R_HID + o, d1[o][0]);
           __syncwarp();
-          tile_gemm<H>(4 + L + PO + 1,
-                       [&](int r) {
+          tile_gemm_r<H, 4 + L + PO + 1>([&](int r) {
                          return r < 4 + L ? rows_state + r * NG
                                           : (r < 4 + L + PO ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
                        },
@@ -646,7 +694,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           stage(R_HID + H, degf);
           __syncwarp();
           // dW4[i][j] += adjS[i] A[j];  db4[i] += deg adjS[i]
-          tile_gemm<H + 1>(PO, [&](int r) { return tile + (R_S + r) * kTS; }, tile + R_HID * kTS, gphi,
+          tile_gemm_r<H + 1, PO>([&](int r) { return tile + (R_S + r) * kTS; }, tile + R_HID * kTS, gphi,
                            [&](int r, int c) { return c < H ? W.phi_w4 + r * HP + c : W.phi_b4 + r; });
           __syncwarp();
           if (MULTI || qq == 2) phi_backward(wphi, gphi);
