@@ -224,6 +224,60 @@ __device__ __forceinline__ void row_dot(float (&out)[VG], const float (&h)[H][VG
     for (int g = 0; g < VG; ++g) out[g] = fmaf(h[o][g], w[o], out[g]);
 }
 
+// ---- TMA (cp.async.bulk) staging of the next batch's raw input rows, tracked by an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned addresses and size), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16-byte aligned window [begin, begin+bytes) covering elements [first, first+count) of a float array
+struct BulkWindow { long long begin; uint32_t bytes; int shift; };   // shift = floats between window start and `first`
+__device__ __forceinline__ BulkWindow bulk_window(long long first, int count) {
+  const long long o = first * 4, oa = o & ~15LL;
+  BulkWindow w;
+  w.begin = oa;
+  w.bytes = (uint32_t)(((o + (long long)count * 4 + 15) & ~15LL) - oa);
+  w.shift = (int)((o - oa) >> 2);
+  return w;
+}
+
+// same de-interleave as load_block, but from the staged raw rows in shared memory
+__device__ __forceinline__ void unpack_block(const float* __restrict__ raw, float* __restrict__ dst, int G, int rows,
+                                             int cols, int c0, int dst_stride, const uint16_t* __restrict__ slot_of_row) {
+  const int per_grid = rows * cols;
+  const int total = per_grid * G;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int gl = idx / per_grid;
+    const int rem = idx - gl * per_grid;
+    const int row = rem / cols;
+    const int c = rem - row * cols;
+    if (c >= c0) {
+      const int slot = slot_of_row ? (int)slot_of_row[row] : row;
+      dst[(c - c0) * dst_stride + slot * G + gl] = raw[idx];
+    }
+  }
+}
+
 // ---- staged input load: reference AoS rows -> grid-interleaved SoA in shared memory ----
 // src: [S][rows][cols]; keeps columns c0..cols-1 as dst[(c-c0)][slot(row)][G] (+gl).
 __device__ __forceinline__ void load_block(const float* __restrict__ src, float* __restrict__ dst,
@@ -287,6 +341,8 @@ struct SmemPlan {          // offsets in floats from the start of dynamic shared
   int red;                 // [nwarps][G]
   int weights;             // [wstep]
   int topo;                // uint16 block (offset in floats)
+  int stage_b, stage_l, stage_g;   // raw AoS staging of the next batch (forward; TMA bulk copies), 0 if unused
+  int mbar;                // one 8-byte mbarrier
   int extra;               // backward-only regions start here
   int total_floats;
 };
@@ -302,6 +358,7 @@ struct FwdArgs {
   int N, Ns, E, Gn, K, NGQ, G, nbatch;   // Ns = bus slots (>= N)
   int NGs, EGs;            // padded row strides of the [.][Ns][G] and [.][E][G] arrays
   int need_grad;
+  int use_tma;             // inputs 16-byte aligned and staging present: prefetch the next batch with cp.async.bulk
   unsigned char grp_of_warp[32];   // warp -> group of 32/NGQ consecutive bus slots
   SmemPlan sm;
   TopoOffsets to;

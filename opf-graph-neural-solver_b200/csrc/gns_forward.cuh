@@ -77,14 +77,63 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const int e_out0 = prim ? (int)t_outb[sl] : 0, e_out1 = prim ? (int)t_oute[sl] : 0;
   const int j0 = prim ? (int)t_genb[sl] : 0, j1 = prim ? (int)t_gene[sl] : 0;
 
+  // ---- TMA staging: the raw rows of batch b+gridDim are bulk-copied while batch b computes ----
+  float* const s_raw_b = smem + a.sm.stage_b;
+  float* const s_raw_l = smem + a.sm.stage_l;
+  float* const s_raw_g = smem + a.sm.stage_g;
+  uint64_t* const s_mbar = reinterpret_cast<uint64_t*>(smem + a.sm.mbar);
+  const bool tma = a.use_tma != 0;
+  uint32_t tma_phase = 0;
+  // a batch takes the bulk path when it is full and its 16-byte windows stay inside the tensors
+  auto bulk_ok = [&](int b) {
+    const long long gb = (long long)b * G;
+    if (!tma || gb + G > a.S) return false;
+    const BulkWindow wb = bulk_window(gb * N * 6, G * N * 6), wl = bulk_window(gb * E * 7, G * E * 7),
+                     wg = bulk_window(gb * Gn * 7, G * Gn * 7);
+    return wb.begin + wb.bytes <= a.S * N * 6 * 4 && wl.begin + wl.bytes <= a.S * E * 7 * 4 &&
+           wg.begin + wg.bytes <= a.S * Gn * 7 * 4;
+  };
+  auto bulk_issue = [&](int b) {     // one thread
+    const long long gb = (long long)b * G;
+    const BulkWindow wb = bulk_window(gb * N * 6, G * N * 6), wl = bulk_window(gb * E * 7, G * E * 7),
+                     wg = bulk_window(gb * Gn * 7, G * Gn * 7);
+    mbar_expect_tx(s_mbar, wb.bytes + wl.bytes + wg.bytes);
+    bulk_g2s(s_raw_b, reinterpret_cast<const char*>(a.buses) + wb.begin, wb.bytes, s_mbar);
+    bulk_g2s(s_raw_l, reinterpret_cast<const char*>(a.lines) + wl.begin, wl.bytes, s_mbar);
+    if (wg.bytes) bulk_g2s(s_raw_g, reinterpret_cast<const char*>(a.gens) + wg.begin, wg.bytes, s_mbar);
+  };
+  if (tma) {
+    if (tid == 0) {
+      mbar_init(s_mbar, 1);
+      fence_proxy_async();
+      if ((int)blockIdx.x < a.nbatch && bulk_ok(blockIdx.x)) bulk_issue(blockIdx.x);
+    }
+    __syncthreads();
+  }
+
   for (int batch = blockIdx.x; batch < a.nbatch; batch += gridDim.x) {
     const long long g0 = (long long)batch * G;
 
     // ---------------- load + de-interleave the G grids of this batch ----------------
-    load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, NG, t_rank);
-    load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, EG, nullptr);
-    load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
+    if (bulk_ok(batch)) {
+      mbar_wait(s_mbar, tma_phase);
+      tma_phase ^= 1;
+      unpack_block(s_raw_b + bulk_window(g0 * N * 6, 0).shift, s_busc, G, N, 6, 2, NG, t_rank);
+      unpack_block(s_raw_l + bulk_window(g0 * E * 7, 0).shift, s_linef, G, E, 7, 2, EG, nullptr);
+      unpack_block(s_raw_g + bulk_window(g0 * Gn * 7, 0).shift, s_genc, G, Gn, 7, 1, GnG, nullptr);
+    } else {
+      load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, NG, t_rank);
+      load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, EG, nullptr);
+      load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
+    }
     __syncthreads();
+    {   // staging buffers are free again: start the copy of this CTA's next batch
+      const int nb_next = batch + gridDim.x;
+      if (tid == 0 && nb_next < a.nbatch && bulk_ok(nb_next)) {
+        fence_proxy_async();
+        bulk_issue(nb_next);
+      }
+    }
 
     // ---------------- state init (ref GNS/main.py:141-152) ----------------
     float part4[4][VG];

@@ -43,7 +43,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, int wstep, int nwarps, int topo_u16,
-                          int extra_floats, bool backward) {
+                          int extra_floats, bool backward, int stage_rows_n /* real buses, 0 = no staging */) {
   SmemPlan s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
@@ -59,6 +59,12 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
   s.red = take(nwarps * G);
   s.weights = take(wstep);
   s.topo = take((topo_u16 + 1) / 2);
+  if (!backward && stage_rows_n > 0) {   // raw staging of the next batch's rows (+ slack for the 16-byte window)
+    s.stage_b = take(G * stage_rows_n * 6 + 8);
+    s.stage_l = take(G * E * 7 + 8);
+    s.stage_g = take(G * Gn * 7 + 8);
+    s.mbar = take(4);
+  }
   s.extra = o;
   o += pad4(extra_floats);
   s.total_floats = o;
@@ -107,6 +113,8 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
   const int force_vg = env_int(backward ? "GNS_BWD_VG" : "GNS_FWD_VG", 0);
   const int force_ngq = env_int(backward ? "GNS_BWD_NGQ" : "GNS_FWD_NGQ", 0);
   const int target_threads = env_int("GNS_TARGET_THREADS", 320);
+  bool use_stage = !backward && !env_int("GNS_NO_TMA", 0);
+  for (int pass = 0; pass < 2 && !found; ++pass, use_stage = false)
   for (int VG : {2, 1}) {
     if (force_vg && VG != force_vg) continue;
     if (backward && VG != 1) continue;          // the backward kernel handles one grid per thread
@@ -125,7 +133,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       g.tmax = (T <= 384) ? 384 : 1024;
       if (g.tmax == 1024 && VG != 1) continue;   // the wide-CTA variant exists for VG=1 only
       const int extra = backward ? backward_extra_floats(N, E, G, md.L, md.H, T) : 0;
-      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward);
+      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, use_stage ? plan->N : 0);
       const size_t bytes = (size_t)sm.total_floats * 4;
       if ((int)bytes > limit) continue;
       g.smem_bytes = bytes; g.sm = sm;

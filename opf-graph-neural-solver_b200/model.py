@@ -194,6 +194,64 @@ class GNS(nn.Module):
         self._last_plan = plan
         return plan
 
+    # ------------------------------------------------------------------ host-resident batches
+    @torch.no_grad()
+    def infer_host(self, buses, lines, generators, out=None, chunk=8192, device=None):
+        """Inference on a HOST-resident batch (ideally pinned): the batch is cut into chunks and the
+        host->device copy of chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1
+        run on three streams, so the end-to-end rate is max(PCIe, compute) instead of their sum.
+        ``out`` = optional (v, theta, total_loss, last_loss) host tensors to fill (pinned for speed).
+        Returns host tensors.  (Not in the reference: it has no batching.)"""
+        if not torch.cuda.is_available():
+            raise RuntimeError("GNS (B200 build) needs a CUDA device: there is no CPU fallback path")
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda":
+            self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+            p0 = next(self.parameters())
+        dev = p0.device
+        S, N = buses.shape[0], buses.shape[1]
+        if out is None:
+            out = (torch.empty(S, N).pin_memory(), torch.empty(S, N).pin_memory(),
+                   torch.empty(S).pin_memory(), torch.empty(S).pin_memory())
+        host_in = (buses, lines, generators)
+        with torch.cuda.device(dev):
+            comp = torch.cuda.current_stream(dev)
+            h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            dbuf = [[torch.empty((chunk,) + tuple(t.shape[1:]), dtype=torch.float32, device=dev) for t in host_in]
+                    for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            free = [torch.cuda.Event() for _ in range(2)]
+            keep = []
+            start = torch.cuda.Event(); start.record(comp)
+            h2d.wait_event(start)
+            flat = self.flat_parameters()
+            params = list(self.parameters())
+            plan = None
+            for i, a in enumerate(range(0, S, chunk)):
+                b = min(S, a + chunk)
+                slot = i % 2
+                with torch.cuda.stream(h2d):
+                    if i >= 2:
+                        h2d.wait_event(free[slot])
+                    for dst, src in zip(dbuf[slot], host_in):
+                        dst[:b - a].copy_(src[a:b], non_blocking=True)
+                    ready[slot].record(h2d)
+                comp.wait_event(ready[slot])
+                d = [t[:b - a] for t in dbuf[slot]]
+                if plan is None:
+                    plan = self.plan_for(d[1], d[2], N)
+                res = _GNSFunction.apply(self, plan, False, d[0], d[1], d[2], flat, *params)
+                free[slot].record(comp)
+                done = torch.cuda.Event(); done.record(comp)
+                d2h.wait_event(done)
+                with torch.cuda.stream(d2h):
+                    for dst, src in zip(out, res):
+                        src.record_stream(d2h)
+                        dst[a:b].copy_(src, non_blocking=True)
+                keep.append(res)
+            d2h.synchronize()
+        return out
+
     # ------------------------------------------------------------------ forward
     def forward(self, buses, lines, generators, B=None, L=None, G=None):
         """Same call as ref GNS/main.py:140.  ``B, L, G`` are accepted for compatibility; the

@@ -127,3 +127,14 @@ def test_negative_voltage_is_clamped_like_the_reference(lib):
     buses, lines, gens, _ = pkg.data.make_batch(14, 3, seed=4)
     got = _check_against_oracle(model, buses, lines, gens, "clamp")
     assert float(got[0].min()) == 0.0
+
+
+def test_infer_host_streams_chunks_and_matches_forward(lib):
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(30, 1000, seed=6)
+    with torch.no_grad():
+        want = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    got = model.infer_host(buses.pin_memory(), lines.pin_memory(), gens.pin_memory(), chunk=192)   # ragged last chunk
+    for g, w in zip(got, want):   # chunks may pick another launch geometry: same math, other summation order
+        assert g.device.type == "cpu" and torch.allclose(g, w.cpu(), rtol=1e-5, atol=1e-6)
