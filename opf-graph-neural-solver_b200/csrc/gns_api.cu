@@ -22,6 +22,32 @@ __global__ void pack_params_kernel(const float* __restrict__ canon, const int32_
     packed[map[i]] = canon[i];
 }
 
+// M[j][o] = sum_i W4[i][j] W1S[i][o],  c[o] = sum_i b4[i] W1S[i][o]  for every step and pair
+// (W1S = rows 4+L.. of the L-net's first layer).  One thread per output element.
+__global__ void fuse_params_kernel(float* __restrict__ packed, WLayout W, int K) {
+  const int per_pair = W.H * W.H + W.H;
+  const int total = K * 3 * per_pair;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int k = t / (3 * per_pair);
+    int r = t - k * 3 * per_pair;
+    const int q = r / per_pair;
+    r -= q * per_pair;
+    float* base = packed + (size_t)k * W.wstep;
+    const float* phi = base + W.off_phi[W.multi ? q : 0];
+    const float* w1s = base + W.off_ln[q] + W.ln_w1 + (4 + W.L) * W.HP;
+    float acc = 0.f;
+    if (r < W.H * W.H) {
+      const int j = r / W.H, o = r - j * W.H;
+      for (int i = 0; i < W.PO; ++i) acc = fmaf(phi[W.phi_w4 + i * W.HP + j], w1s[i * W.HP + o], acc);
+      base[W.off_mf[q] + j * W.HP + o] = acc;
+    } else {
+      const int o = r - W.H * W.H;
+      for (int i = 0; i < W.PO; ++i) acc = fmaf(phi[W.phi_b4 + i], w1s[i * W.HP + o], acc);
+      base[W.off_mf[q] + W.H * W.HP + o] = acc;
+    }
+  }
+}
+
 __global__ void check_topology_kernel(const float* __restrict__ lines, const float* __restrict__ gens,
                                       const float* __restrict__ expect, long long S, int E, int Gn, int* flag) {
   const long long per = 2LL * E + Gn;
@@ -157,6 +183,9 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
     const int th = 256;
     const int bl = (int)std::min<int64_t>((pm->n_canon + th - 1) / th, 1024);
     pack_params_kernel<<<bl, th, 0, st>>>(params, pm->d_map, packed, pm->n_canon);
+    const WLayout Wl = make_wlayout(L, H, multi != 0);
+    const int tot = K * 3 * (H * H + H);
+    fuse_params_kernel<<<(tot + th - 1) / th, th, 0, st>>>(packed, Wl, K);
   }
   FwdLauncher launch = find_forward(L, H, multi, gf.VG, gf.tmax);
   if (!launch) { set_error("gns_forward: kernel variant not built"); return -1; }

@@ -37,6 +37,48 @@ __global__ void reduce_partials_kernel(const float* __restrict__ gacc, float* __
   }
 }
 
+// Chain rule of the fused aggregate->hidden block back to the parameters it was built from:
+//   dW4[i][j]  = sum_o W1S[i][o] dM[j][o]
+//   dW1S[i][o] = sum_j W4[i][j] dM[j][o] + b4[i] dc[o]
+//   db4[i]     = sum_o W1S[i][o] dc[o]
+// (single phi: W4 / b4 are shared by the three pairs and receive the sum).  One thread per
+// destination element; these rows get no other contribution.
+__global__ void unfuse_grads_kernel(float* __restrict__ grad, const float* __restrict__ packed, WLayout W, int K) {
+  const int nphi = W.multi ? 3 : 1;
+  const int n_w4 = nphi * W.PO * W.H, n_b4 = nphi * W.PO, n_w1s = 3 * W.PO * W.H;
+  const int per_step = n_w4 + n_b4 + n_w1s;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K * per_step; t += gridDim.x * blockDim.x) {
+    const int k = t / per_step;
+    int r = t - k * per_step;
+    const float* pb = packed + (size_t)k * W.wstep;
+    float* gb = grad + (size_t)k * W.wstep;
+    if (r < n_w4 + n_b4) {
+      const bool is_b = r >= n_w4;
+      if (is_b) r -= n_w4;
+      const int p = is_b ? r / W.PO : r / (W.PO * W.H);
+      const int rem = is_b ? r - p * W.PO : r - p * W.PO * W.H;
+      const int i = is_b ? rem : rem / W.H, j = is_b ? 0 : rem - (rem / W.H) * W.H;
+      float acc = 0.f;
+      for (int q = (W.multi ? p : 0); q < (W.multi ? p + 1 : 3); ++q) {
+        const float* w1s = pb + W.off_ln[q] + W.ln_w1 + (4 + W.L) * W.HP + i * W.HP;
+        const float* dm = gb + W.off_mf[q] + (is_b ? W.H * W.HP : j * W.HP);
+        for (int o = 0; o < W.H; ++o) acc = fmaf(w1s[o], dm[o], acc);
+      }
+      gb[W.off_phi[p] + (is_b ? W.phi_b4 + i : W.phi_w4 + i * W.HP + j)] = acc;
+    } else {
+      r -= n_w4 + n_b4;
+      const int q = r / (W.PO * W.H);
+      const int rem = r - q * W.PO * W.H;
+      const int i = rem / W.H, o = rem - i * W.H;
+      const float* phi = pb + W.off_phi[W.multi ? q : 0];
+      const float* dm = gb + W.off_mf[q];
+      float acc = phi[W.phi_b4 + i] * dm[W.H * W.HP + o];
+      for (int j = 0; j < W.H; ++j) acc = fmaf(phi[W.phi_w4 + i * W.HP + j], dm[j * W.HP + o], acc);
+      gb[W.off_ln[q] + W.ln_w1 + (4 + W.L + i) * W.HP + o] = acc;
+    }
+  }
+}
+
 // canon[c] = packed[map[c]]
 __global__ void unpack_grads_kernel(const float* __restrict__ packed, const int32_t* __restrict__ map,
                                     float* __restrict__ canon, long long n) {
@@ -95,6 +137,9 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
     const int th = 256;
     const int bl = (int)std::min<long long>(((long long)per_part + th - 1) / th, 2048);
     reduce_partials_kernel<<<bl, th, 0, st>>>(gacc, packed_grad, (long long)per_part, nparts);
+    const int nphi = md.multi ? 3 : 1, PO = md.multi ? md.L : 1;
+    const int tot = md.K * (nphi * PO * md.H + nphi * PO + 3 * PO * md.H);
+    unfuse_grads_kernel<<<(tot + th - 1) / th, th, 0, st>>>(packed_grad, a.params, W, md.K);
     const int bl2 = (int)std::min<long long>((pm->n_canon + th - 1) / th, 1024);
     unpack_grads_kernel<<<bl2, th, 0, st>>>(packed_grad, pm->d_map, grad_params, pm->n_canon);
   }

@@ -40,7 +40,7 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
   int total;
 };
 
-__host__ __device__ inline int bwd_tile_rows(int H, int PO) { return 1 + (H + 1) + 16 + (PO > H + 1 ? PO : H + 1); }
+__host__ __device__ inline int bwd_tile_rows(int H, int /*PO*/) { return 1 + (H + 1) + 16 + (H + 1); }
 
 __host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps) {
   BwdSmem b{};
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   constexpr int R_ONES = 0;
   constexpr int R_HID = 1;                 // H+1 rows
   constexpr int R_WIDE = R_HID + H + 1;    // 16 rows
-  constexpr int R_S = R_WIDE + 16;         // max(PO, H+1) rows: S_i / adjoint of S_i ...
+  constexpr int R_S = R_WIDE + 16;         // H+1 rows: the aggregate A and the in-degree (wide rows of dM / dc) ...
   constexpr int R_HID2 = R_S;              // ... and, once those are dead (phi adjoint), a second hid block
   static_assert(H + 1 + 5 <= 16, "wide staging rows");
 
@@ -579,15 +579,17 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll 4
           for (int i = 0; i < L; ++i) { float x[1] = {sm_m[i * NG]}; row_axpy<H, HP, 1>(zL, x, wln + W.ln_w1 + (4 + i) * HP); }
           __syncwarp();
+          const float* wmf = s_w + W.off_mf[0] + q * W.mf_size;     // fused block M (H rows) and c (1 row)
           {
-            float (&Av)[H][1] = reinterpret_cast<float (&)[H][1]>(A);
-#pragma unroll 2
-            for (int i = 0; i < PO; ++i) {
-              float sv[1] = {degf * wphi[W.phi_b4 + i]};
-              row_dot<H, HP, 1>(sv, Av, wphi + W.phi_w4 + i * HP);
-              stage(R_S + i, sv[0]);
-              row_axpy<H, HP, 1>(zL, sv, wln + W.ln_w1 + (4 + L + i) * HP);
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              float aj[1] = {A[j]};
+              row_axpy<H, HP, 1>(zL, aj, wmf + j * HP);
+              stage(R_S + j, A[j]);                                  // wide rows of dM
             }
+            float dg[1] = {degf};
+            row_axpy<H, HP, 1>(zL, dg, wmf + H * HP);
+            stage(R_S + H, degf);                                    // wide row of dc
           }
           float h1L[H][1], h2L[H][1];
           {
@@ -655,12 +657,19 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
           for (int o = 0; o < H; ++o) stage(R_HID + o, d1[o][0]);
           __syncwarp();
-          tile_gemm_r<H, 4 + L + PO + 1>([&](int r) {
-                         return r < 4 + L ? rows_state + r * NG
-                                          : (r < 4 + L + PO ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
-                       },
-                       tile + R_HID * kTS, gln,
-                       [&](int r, int c) { return (r < 4 + L + PO ? W.ln_w1 + r * HP : W.ln_b1) + c; });
+          {
+            const int mf_rel = (W.off_mf[0] + q * W.mf_size) - (W.off_ln[0] + q * W.ln_size_s);   // dM / dc block, relative to gln
+            // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
+            tile_gemm_r<H, 4 + L + H + 2>(
+                [&](int r) {
+                  return r < 4 + L ? rows_state + r * NG
+                                   : (r < 4 + L + H + 1 ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
+                },
+                tile + R_HID * kTS, gln,
+                [&](int r, int c) {
+                  return (r < 4 + L ? W.ln_w1 + r * HP : (r < 4 + L + H + 1 ? mf_rel + (r - 4 - L) * HP : W.ln_b1)) + c;
+                });
+          }
           __syncwarp();
           // ---- dX of the first layer ----
 #pragma unroll
@@ -679,23 +688,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
             for (int o = 0; o < H; ++o) adjA[o] = 0.f;
           }
-          {
-            float (&aAv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjA);
-#pragma unroll 2
-            for (int i = 0; i < PO; ++i) {
-              float t[1] = {0.f};
-              row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + L + i) * HP);
-              stage(R_S + i, t[0]);                                  // adjoint of S_i
-              row_axpy<H, HP, 1>(aAv, t, wphi + W.phi_w4 + i * HP);
-            }
-          }
 #pragma unroll
-          for (int o = 0; o < H; ++o) stage(R_HID + o, A[o]);
-          stage(R_HID + H, degf);
-          __syncwarp();
-          // dW4[i][j] += adjS[i] A[j];  db4[i] += deg adjS[i]
-          tile_gemm_r<H + 1, PO>([&](int r) { return tile + (R_S + r) * kTS; }, tile + R_HID * kTS, gphi,
-                           [&](int r, int c) { return c < H ? W.phi_w4 + r * HP + c : W.phi_b4 + r; });
+          for (int j = 0; j < H; ++j) {       // adjoint of the aggregate through the fused block: adjA[j] += M[j] . d1
+            float t[1] = {0.f};
+            row_dot<H, HP, 1>(t, d1, wmf + j * HP);
+            adjA[j] += t[0];
+          }
           __syncwarp();
           if (MULTI || qq == 2) phi_backward(wphi, gphi);
         }

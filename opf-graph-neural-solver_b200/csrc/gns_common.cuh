@@ -39,8 +39,11 @@ struct WLayout {
   int phi_w1m, phi_w1f, phi_b1, phi_w2, phi_b2, phi_w4, phi_b4, phi_size;
   // inside an L-net block
   int ln_w1, ln_b1, ln_w2, ln_b2, ln_wo, ln_bo_s, ln_bo_m, ln_size_s, ln_size_m;
-  // step block: phi nets in pair order (v, theta, m | single), then L_v, L_theta, L_m
-  int off_phi[3], off_ln[3], wstep;
+  // step block: phi nets in pair order (v, theta, m | single), then L_v, L_theta, L_m, then the
+  // fused aggregate->hidden blocks of the three pairs:  M[j][o] = sum_i W4[i][j] * W1_L[4+L+i][o]
+  // ([H][HP]) followed by c[o] = sum_i b4[i] * W1_L[4+L+i][o] ([HP]).  They are derived from the
+  // parameters after packing (forward) and carry dM / dc in the gradient buffer (backward).
+  int off_phi[3], off_ln[3], off_mf[3], mf_size, wparams, wstep;
 };
 
 __host__ __device__ constexpr WLayout make_wlayout(int L, int H, bool multi) {
@@ -75,6 +78,9 @@ __host__ __device__ constexpr WLayout make_wlayout(int L, int H, bool multi) {
   w.off_ln[0] = o; o += w.ln_size_s;
   w.off_ln[1] = o; o += w.ln_size_s;
   w.off_ln[2] = o; o += w.ln_size_m;
+  w.wparams = o;                       // floats that map 1:1 to parameters (+ padding)
+  w.mf_size = H * w.HP + w.HP;
+  for (int q = 0; q < 3; ++q) { w.off_mf[q] = o; o += w.mf_size; }
   w.wstep = o;
   return w;
 }

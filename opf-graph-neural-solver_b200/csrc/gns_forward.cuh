@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             }
           }
           if (!prim) continue;
-          const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
           float zL[H][VG];
           {
@@ -333,14 +332,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             IO::ld(x, sm_m + i * NG);
             row_axpy<H, HP, VG>(zL, x, wln + W.ln_w1 + (4 + i) * HP);
           }
-#pragma unroll 2
-          for (int i = 0; i < PO; ++i) {
-            float s[VG];
-            const float b4 = wphi[W.phi_b4 + i];
+          {   // S = W4 A + deg b4 feeds the first layer linearly: use the pre-multiplied block
+              // M = W4^T W1[:, 4+L:]^T and c = b4 W1[:, 4+L:]^T (fuse_params_kernel): H*H instead of 2*L*H MACs
+            const float* wmf = s_w + W.off_mf[0] + q * W.mf_size;
 #pragma unroll
-            for (int g = 0; g < VG; ++g) s[g] = degf * b4;
-            row_dot<H, HP, VG>(s, A, wphi + W.phi_w4 + i * HP);
-            row_axpy<H, HP, VG>(zL, s, wln + W.ln_w1 + (4 + L + i) * HP);
+            for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(zL, A[j], wmf + j * HP);
+            float dg[VG];
+#pragma unroll
+            for (int g = 0; g < VG; ++g) dg[g] = degf;
+            row_axpy<H, HP, VG>(zL, dg, wmf + H * HP);
           }
           float z2[H][VG];
           {
