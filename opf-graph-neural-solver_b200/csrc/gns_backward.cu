@@ -12,7 +12,7 @@ BwdLauncher find_backward(int L, int H, int multi, int tmax);
 
 int backward_extra_floats(int N, int E, int G, int L, int H, int T) {
   // PO <= L: size the tiles for the multiple-phi case
-  return make_bwd_smem(N, E, G, L, H, L, T / 32).total;
+  return make_bwd_smem(N, E, G, L, H, L, T / 32, L > 32).total;
 }
 
 int backward_ctas(const gns_plan* plan, const ModelDims&, const Geometry& g) {
@@ -128,7 +128,8 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G);
   std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);
   a.sm = gb.sm;
-  a.bs = make_bwd_smem(plan->Ns, plan->E, gb.G, md.L, md.H, md.L, nwarps);
+  a.bs = make_bwd_smem(plan->Ns, plan->E, gb.G, md.L, md.H, md.L, nwarps, md.L > 32);
+  a.mscratch = md.L > 32 ? reinterpret_cast<float*>(wsb + ws.mscratch) : nullptr;
   a.to = plan->to;
   for (int k = 0; k < md.K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(md.K - k));
   e = launch(a, gb, st);

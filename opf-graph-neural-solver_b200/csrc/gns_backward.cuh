@@ -42,11 +42,12 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
 
 __host__ __device__ inline int bwd_tile_rows(int H, int /*PO*/) { return 1 + (H + 1) + 16 + (H + 1); }
 
-__host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps) {
+__host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps,
+                                                bool mglobal = false) {
   BwdSmem b{};
   const int NGs = row_stride(N * G), EGs = row_stride(E * G);
   int o = 0;
-  b.adj = o; o += (4 + L) * NGs;
+  b.adj = o; o += (mglobal ? 4 : 4 + L) * NGs;   // large latent: m / adj m rows live in a global scratch instead
   b.nxt = o; o += 4 * NGs;
   b.lineg = o; o += 5 * EGs;
   b.adjD = o; o += NGs;
@@ -63,6 +64,7 @@ struct BwdArgs {
   const float* pglob;       // [nbatch_f][K][G_f]
   const float* grad_total; const float* grad_last; const float* grad_v; const float* grad_theta;
   float* gacc;              // [ctas*nwarps][K*wstep] per-warp gradient accumulators (zeroed by the host)
+  float* mscratch;          // [ctas][2][L][NGs] m and adj m rows when they do not fit shared memory (L > 32)
   const uint16_t* topo;
   long long S;
   int N, Ns, E, Gn, K, NGQ, G, nbatch;
@@ -141,8 +143,13 @@ __device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict
   }
 }
 
+// Large latent dimensions (L > 32): state m and its adjoint (2 x L x Ns floats, 183 KB for L=64 on
+// case300) do not fit next to the tiles, so both live in an L2-resident per-CTA global scratch with
+// the same [feature][item] layout; they are only ever touched by the owning thread (the message
+// uses the receiver's own latent) and by the in-place rows of the weight-gradient tiles.
 template <int L, int H, bool MULTI, int TMAX>
 __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) {
+  constexpr bool MG = L > 32;
   constexpr WLayout W = make_wlayout(L, H, MULTI);
   constexpr int HP = pad4(H);
   constexpr int PO = MULTI ? L : 1;
@@ -170,6 +177,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   float* const s_nxt = smem + a.sm.extra + a.bs.nxt;
   float* const s_lineg = smem + a.sm.extra + a.bs.lineg;
   float* const s_adjD = smem + a.sm.extra + a.bs.adjD;
+  // rows of m / adj m: [i][NGs]
+  float* const m_rows = MG ? a.mscratch + (size_t)blockIdx.x * 2 * L * a.NGs : s_state + 4 * a.NGs;
+  float* const am_rows = MG ? a.mscratch + ((size_t)blockIdx.x * 2 + 1) * L * a.NGs : s_adj + 4 * a.NGs;
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int grp = a.grp_of_warp[warp];                 // bus group of this warp (sub-partition balancing)
@@ -263,7 +273,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       const int ext = t_ext[n];
       s_adj[0 * NG + nb] = (grid_ok && a.grad_v) ? a.grad_v[gld * N + ext] : 0.f;
       s_adj[1 * NG + nb] = (grid_ok && a.grad_theta) ? a.grad_theta[gld * N + ext] : 0.f;
-      for (int i = 2; i < 4 + L; ++i) s_adj[i * NG + nb] = 0.f;
+      s_adj[2 * NG + nb] = 0.f; s_adj[3 * NG + nb] = 0.f;
+      for (int i = 0; i < L; ++i) am_rows[i * NG + nb] = 0.f;
       const float* ck = ck_base + (size_t)(K - 1) * ck_stride + (size_t)n * a.Gf;
       for (int i = 0; i < 4; ++i) s_nxt[i * NG + nb] = ck[(size_t)i * a.NGs_f];
     }
@@ -286,7 +297,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       if (bus_on) {
         if (k >= 1) {
           const float* ck = ck_base + (size_t)(k - 1) * ck_stride + (size_t)n * a.Gf;
-          for (int i = 0; i < 4 + L; ++i) s_state[i * NG + nb] = ck[(size_t)i * a.NGs_f];
+          for (int i = 0; i < 4; ++i) s_state[i * NG + nb] = ck[(size_t)i * a.NGs_f];
+          for (int i = 0; i < L; ++i) m_rows[i * NG + nb] = ck[(size_t)(4 + i) * a.NGs_f];
         } else {   // state before step 0 (ref GNS/main.py:141-152)
           float vv = 0.f, pg = 0.f, qg = 0.f;
           for (int j = j0; j < j1; ++j) {
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           s_state[1 * NG + nb] = 0.f;
           s_state[2 * NG + nb] = pg - s_busc[0 * NG + nb] - s_busc[2 * NG + nb] * (vv * vv);
           s_state[3 * NG + nb] = qg - s_busc[1 * NG + nb] + s_busc[3 * NG + nb] * (vv * vv);
-          for (int i = 0; i < L; ++i) s_state[(4 + i) * NG + nb] = 0.f;
+          for (int i = 0; i < L; ++i) m_rows[i * NG + nb] = 0.f;
         }
       }
 
@@ -405,14 +417,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       float* const gk = gacc_w + (size_t)k * W.wstep;
       {
         const float* st = s_state + nb;
-        const float* sm_m = st + 4 * NG;
+        const float* sm_m = m_rows + nb;
         float* adjrow = s_adj + nb;
+        float* adjm = am_rows + nb;
         float st4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) st4[i] = st[i * NG];
         float adj4[4] = {0.f, 0.f, 0.f, 0.f};
         const float* rows_state = s_state + 32 * grp;          // [f][item] rows of this warp's 32 items
-        const float* rows_adj = s_adj + 32 * grp;
+        const float* rows_m = m_rows + 32 * grp;
+        const float* rows_am = am_rows + 32 * grp;
         float A[H], P[H], adjA[H];
 #pragma unroll
         for (int o = 0; o < H; ++o) { A[o] = 0.f; P[o] = 0.f; adjA[o] = 0.f; }
@@ -543,7 +557,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int o = 0; o < H; ++o) stage(R_HID + o, adjP[o]);
           __syncwarp();
           // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
-          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_state + (4 + r) * NG : tile + R_ONES * kTS; },
+          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * NG : tile + R_ONES * kTS; },
                        tile + R_HID * kTS, gphi,
                        [&](int r, int c) { return (r < L ? W.phi_w1m + r * HP : W.phi_b1) + c; });
           {
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             for (int i = 0; i < L; ++i) {
               float t[1] = {0.f};
               row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
-              if (bus_on) adjrow[(4 + i) * NG] += t[0];
+              if (bus_on) adjm[i * NG] += t[0];
             }
           }
         };
@@ -622,7 +636,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           } else {
 #pragma unroll 2
             for (int i = 0; i < L; ++i) {
-              float gm[1] = {bus_on ? adjrow[(4 + i) * NG] : 0.f};
+              float gm[1] = {bus_on ? adjm[i * NG] : 0.f};
               row_axpy<H, HP, 1>(dh2, gm, wln + W.ln_wo + i * HP);
             }
 #pragma unroll
@@ -630,7 +644,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             stage(R_HID + H, 1.f);
             __syncwarp();
             // dWout[i][j] += adjm'[i] h2[j];  dbout[i] += adjm'[i]    (rows = adj m' rows in place)
-            tile_gemm_r<H + 1, L>([&](int r) { return rows_adj + (4 + r) * NG; }, tile + R_HID * kTS, gln,
+            tile_gemm_r<H + 1, L>([&](int r) { return rows_am + r * NG; }, tile + R_HID * kTS, gln,
                              [&](int r, int c) { return c < H ? W.ln_wo + r * HP + c : W.ln_bo_m + r; });
           }
           __syncwarp();
@@ -662,7 +676,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
             tile_gemm_r<H, 4 + L + H + 2>(
                 [&](int r) {
-                  return r < 4 + L ? rows_state + r * NG
+                  return r < 4 ? rows_state + r * NG
+                         : r < 4 + L ? rows_m + (r - 4) * NG
                                    : (r < 4 + L + H + 1 ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
                 },
                 tile + R_HID * kTS, gln,
@@ -682,7 +697,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int i = 0; i < L; ++i) {
             float t[1] = {0.f};
             row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
-            if (bus_on) adjrow[(4 + i) * NG] += t[0];
+            if (bus_on) adjm[i * NG] += t[0];
           }
           if (MULTI) {
 #pragma unroll

@@ -54,6 +54,7 @@ struct Workspace {
   size_t pglob = 0;           // [nbatch][K][G] floats                 (need_grad)
   size_t gpartial = 0;        // [ctas][K][wstep] floats               (need_grad): per-CTA gradient partial sums
   size_t packed_grad = 0;     // [K][wstep] floats                     (need_grad)
+  size_t mscratch = 0;        // [ctas][2][L][NGs] floats              (need_grad, L > 32)
   size_t total = 0;
 };
 

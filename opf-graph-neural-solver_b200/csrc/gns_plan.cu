@@ -43,12 +43,14 @@ static int env_int(const char* name, int dflt) {
 }
 
 static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, int wstep, int nwarps, int topo_u16,
-                          int extra_floats, bool backward, int stage_rows_n /* real buses, 0 = no staging */) {
+                          int extra_floats, bool backward, int stage_rows_n /* real buses, 0 = no staging */,
+                          int state_rows) {
   SmemPlan s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
   const int NGs = row_stride(N * G), EGs = row_stride(E * G);
-  s.state = take((4 + L) * NGs);
+  (void)L;
+  s.state = take(state_rows * NGs);
   s.busc = take(4 * NGs);
   s.genc = take(6 * Gn * G);
   s.linef = take(5 * EGs);
@@ -133,7 +135,8 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       g.tmax = (T <= 384) ? 384 : 1024;
       if (g.tmax == 1024 && VG != 1) continue;   // the wide-CTA variant exists for VG=1 only
       const int extra = backward ? backward_extra_floats(N, E, G, md.L, md.H, T) : 0;
-      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, use_stage ? plan->N : 0);
+      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, use_stage ? plan->N : 0,
+                                      (backward && md.L > 32) ? 4 : 4 + md.L);
       const size_t bytes = (size_t)sm.total_floats * 4;
       if ((int)bytes > limit) continue;
       g.smem_bytes = bytes; g.sm = sm;
@@ -237,6 +240,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * W.wstep * 4);   // one block per warp
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
+    if (md.L > 32) { w.mscratch = o; o = align(o + (size_t)bwd.ctas * 2 * md.L * row_stride(plan->Ns * bwd.G) * 4); }
   }
   w.total = o;
   return w;

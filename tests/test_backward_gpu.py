@@ -31,8 +31,7 @@ def per_tensor_report(got, want):
     return "\n".join(f"{r[1]:32s} err {r[2]:.3e}  max|g| {r[3]:.3e}" for r in rows[:12])
 
 
-@pytest.mark.parametrize("path", [p for p in golden_files() if "l64" not in p],
-                         ids=lambda p: p.split("ref_case14_")[-1][:-4])
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("ref_case14_")[-1][:-4])
 def test_gradients_match_reference_autograd(lib, path):
     g = load_golden(path)
     model = _model_from(g["params"], g["latent_dim"], g["hidden_dim"], g["K"], g["gamma"], g["multiple_phi"])
@@ -63,6 +62,25 @@ def test_gradients_vs_oracle_autograd(lib, n_bus, S, multi):
     got = _grads(model)
     try:
         assert_grads_close(got, want, f"case{n_bus}")
+    except AssertionError:
+        print(per_tensor_report(got, want))
+        raise
+
+
+def test_stress_config_k8_l64_gradients_case300(lib):
+    """BASELINE configs[4]: case300, K=8, latent 64 (m / adj m rows live in the global scratch)."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=64, hidden_dim=10, K=8, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(300, 3, seed=3)
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    (_, _, otot, _), want = orc.gns_loss_and_grads(params, buses.double(), lines.double(), gens.double(), K=8,
+                                                   latent_dim=64, gamma=0.9, multiple_phi=True)
+    out = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    out[2].mean().backward()
+    assert_loss_close(out[2], otot, "total")
+    got = _grads(model)
+    try:
+        assert_grads_close(got, want, "case300 K8 L64")
     except AssertionError:
         print(per_tensor_report(got, want))
         raise
