@@ -116,6 +116,8 @@ int gns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * FFMA kernel for about `iters` dependent-chain rounds and returns achieved FLOP/s
  * (synchronises the device). */
 double gns_measure_ffma_flops(int device, int iters);
+/* Same probe issued as packed FFMA2 (fma.rn.f32x2, two FMAs per lane per instruction). */
+double gns_measure_ffma2_flops(int device, int iters);
 
 const char* gns_last_error(void);
 const char* gns_version(void);

@@ -11,7 +11,7 @@ _LIB = None
 SYMBOLS = [
     "gns_plan_create", "gns_plan_destroy", "gns_plan_export", "gns_dims_supported",
     "gns_param_count", "gns_workspace_bytes", "gns_forward", "gns_backward",
-    "gns_check_topology", "gns_launch_info", "gns_adam_step", "gns_measure_ffma_flops",
+    "gns_check_topology", "gns_launch_info", "gns_adam_step", "gns_measure_ffma_flops", "gns_measure_ffma2_flops",
     "gns_last_error", "gns_version",
 ]
 
@@ -69,6 +69,8 @@ def load_library():
     lib.gns_adam_step.restype = i32
     lib.gns_measure_ffma_flops.argtypes = [i32, i32]
     lib.gns_measure_ffma_flops.restype = C.c_double
+    lib.gns_measure_ffma2_flops.argtypes = [i32, i32]
+    lib.gns_measure_ffma2_flops.restype = C.c_double
     lib.gns_last_error.argtypes = []
     lib.gns_last_error.restype = C.c_char_p
     lib.gns_version.argtypes = []

@@ -97,6 +97,25 @@ __global__ void ffma_probe_kernel(float* out, int iters, float a, float b) {
   if (s == 123.456f) out[0] = s;   // keep the loop alive
 }
 
+// same probe with the packed FFMA2 (fma.rn.f32x2) instruction of sm_100: 2 FMAs per lane per issue slot
+__global__ void ffma2_probe_kernel(float* out, int iters, float a, float b) {
+  float2 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-6f + i, threadIdx.x * 2e-6f + i);
+  const float2 bb = make_float2(b, b);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], make_float2(a, a), bb);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
 static bool check_plan(const gns_plan* plan) {
   if (plan && plan->device < 0) { set_error("host-only plan (device < 0) cannot launch kernels"); return false; }
   return plan != nullptr;
@@ -255,6 +274,34 @@ extern "C" int gns_adam_step(float* params, const float* grads, float* exp_avg, 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("adam launch: ") + cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+extern "C" double gns_measure_ffma2_flops(int device, int iters) {
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return -1.0; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  float* d = nullptr;
+  cudaMalloc(&d, 4);
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  ffma2_probe_kernel<<<blocks, threads>>>(d, iters / 4 + 1, 1.0000001f, 1e-9f);
+  cudaDeviceSynchronize();
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    ffma2_probe_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 2 * 8 * 8 * (double)iters * threads * (double)blocks;
+    best = std::max(best, flops / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  if (cudaGetLastError() != cudaSuccess) { set_error("ffma2 probe failed"); return -1.0; }
+  return best;
 }
 
 extern "C" double gns_measure_ffma_flops(int device, int iters) {

@@ -102,16 +102,21 @@ __device__ __forceinline__ void tile_gemm_chunk(int rb, int re, RowFn rowfn, con
     for (int c = 0; c < C; ++c) old[c] = writer ? g[outfn(r, c)] : 0.f;
 #endif
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float2 acc2[C];                      // item pairs per column: FFMA2, folded at the end
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc2[c] = make_float2(0.f, 0.f);
 #pragma unroll 2
     for (int q = 0; q < QP; ++q) {
       const float4 av = a4[q];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float4 h = *reinterpret_cast<const float4*>(h0 + c * kTS + 4 * q);
-        acc[c] = fmaf(av.x, h.x, fmaf(av.y, h.y, fmaf(av.z, h.z, fmaf(av.w, h.w, acc[c]))));
+        acc2[c] = fma2(make_float2(av.x, av.y), make_float2(h.x, h.y), acc2[c]);
+        acc2[c] = fma2(make_float2(av.z, av.w), make_float2(h.z, h.w), acc2[c]);
       }
     }
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = acc2[c].x + acc2[c].y;
     if (PARTS > 1) {
 #pragma unroll
       for (int d = RW; d < 32; d *= 2) {

@@ -208,26 +208,67 @@ __device__ __forceinline__ void load_row(float (&w)[HP], const float* row) {
   }
 }
 
+// Packed FP32 pairs: sm_100 issues two FMAs per lane in one FFMA2 (fma.rn.f32x2) and accepts a
+// scalar register as a broadcast operand, so a weight-times-two-grids (VG=2) or a
+// two-weights-times-one-activation (VG=1) update costs one issue slot instead of two.  Measured
+// FFMA2 peak on B200 = FFMA peak (74.0 vs 72.3 TFLOP/s): the freed issue slots go to LDS / ALU work.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 // acc[o][g] += x[g] * row[o]
 template <int H, int HP, int VG>
 __device__ __forceinline__ void row_axpy(float (&acc)[H][VG], const float (&x)[VG], const float* row) {
   float w[HP];
   load_row<HP>(w, row);
+  if constexpr (VG == 2) {
+    const float2 xv = make_float2(x[0], x[1]);
 #pragma unroll
-  for (int o = 0; o < H; ++o)
+    for (int o = 0; o < H; ++o) {
+      const float2 r = fma2(xv, make_float2(w[o], w[o]), make_float2(acc[o][0], acc[o][1]));
+      acc[o][0] = r.x; acc[o][1] = r.y;
+    }
+  } else if constexpr (VG == 1) {
+    const float2 xv = make_float2(x[0], x[0]);
 #pragma unroll
-    for (int g = 0; g < VG; ++g) acc[o][g] = fmaf(x[g], w[o], acc[o][g]);
+    for (int o = 0; o + 1 < H; o += 2) {
+      const float2 r = fma2(make_float2(w[o], w[o + 1]), xv, make_float2(acc[o][0], acc[o + 1][0]));
+      acc[o][0] = r.x; acc[o + 1][0] = r.y;
+    }
+    if (H & 1) acc[H - 1][0] = fmaf(x[0], w[H - 1], acc[H - 1][0]);
+  } else {
+#pragma unroll
+    for (int o = 0; o < H; ++o)
+#pragma unroll
+      for (int g = 0; g < VG; ++g) acc[o][g] = fmaf(x[g], w[o], acc[o][g]);
+  }
 }
 
-// out[g] = init[g] + sum_o h[o][g] * row[o]
+// out[g] += sum_o h[o][g] * row[o]
 template <int H, int HP, int VG>
 __device__ __forceinline__ void row_dot(float (&out)[VG], const float (&h)[H][VG], const float* row) {
   float w[HP];
   load_row<HP>(w, row);
+  if constexpr (VG == 2) {
+    float2 t0 = make_float2(out[0], out[1]), t1 = make_float2(0.f, 0.f);   // two chains: shorter dependency
 #pragma unroll
-  for (int o = 0; o < H; ++o)
+    for (int o = 0; o + 1 < H; o += 2) {
+      t0 = fma2(make_float2(h[o][0], h[o][1]), make_float2(w[o], w[o]), t0);
+      t1 = fma2(make_float2(h[o + 1][0], h[o + 1][1]), make_float2(w[o + 1], w[o + 1]), t1);
+    }
+    if (H & 1) t0 = fma2(make_float2(h[H - 1][0], h[H - 1][1]), make_float2(w[H - 1], w[H - 1]), t0);
+    out[0] = t0.x + t1.x; out[1] = t0.y + t1.y;
+  } else if constexpr (VG == 1) {
+    float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int g = 0; g < VG; ++g) out[g] = fmaf(h[o][g], w[o], out[g]);
+    for (int o = 0; o + 1 < H; o += 2) t = fma2(make_float2(h[o][0], h[o + 1][0]), make_float2(w[o], w[o + 1]), t);
+    float r = out[0] + (t.x + t.y);
+    if (H & 1) r = fmaf(h[H - 1][0], w[H - 1], r);
+    out[0] = r;
+  } else {
+#pragma unroll
+    for (int o = 0; o < H; ++o)
+#pragma unroll
+      for (int g = 0; g < VG; ++g) out[g] = fmaf(h[o][g], w[o], out[g]);
+  }
 }
 
 // ---- TMA (cp.async.bulk) staging of the next batch's raw input rows, tracked by an mbarrier ----
