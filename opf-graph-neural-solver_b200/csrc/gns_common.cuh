@@ -389,7 +389,9 @@ struct SmemPlan {          // offsets in floats from the start of dynamic shared
   int weights;             // [wstep]
   int topo;                // uint16 block (offset in floats)
   int stage_b, stage_l, stage_g;   // raw AoS staging of the next batch (forward; TMA bulk copies), 0 if unused
-  int mbar;                // one 8-byte mbarrier
+  int mbar;                // 8-byte mbarrier of the input staging
+  int weights2;            // second weight buffer (TMA double buffering of the per-step weights), 0 if unused
+  int mbar_w;              // its mbarrier
   int extra;               // backward-only regions start here
   int total_floats;
 };

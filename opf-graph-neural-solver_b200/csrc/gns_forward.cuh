@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   float* const s_flow = smem + a.sm.flows;
   float* const s_gsum = smem + a.sm.gsum;
   float* const s_red = smem + a.sm.red;
-  float* const s_w = smem + a.sm.weights;
+  // current step's weights: offset select on the shared-memory base (keeps the address space provable;
+  // a pointer picked from an array of pointers degrades every weight load to a generic LD)
+  const float* s_w = smem + a.sm.weights;
   uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
 
   const int tid = threadIdx.x, T = blockDim.x;
@@ -102,11 +104,21 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     bulk_g2s(s_raw_l, reinterpret_cast<const char*>(a.lines) + wl.begin, wl.bytes, s_mbar);
     if (wg.bytes) bulk_g2s(s_raw_g, reinterpret_cast<const char*>(a.gens) + wg.begin, wg.bytes, s_mbar);
   };
+  // per-step weights: double-buffered bulk copies, step t+1 is in flight while step t computes
+  uint64_t* const s_mbar_w = reinterpret_cast<uint64_t*>(smem + a.sm.mbar_w);
+  const bool tma_w = tma && a.sm.weights2 != 0;
+  uint32_t w_phase = 0, w_buf = 0;
+  auto weights_issue = [&](int k, int buf) {   // one thread
+    mbar_expect_tx(s_mbar_w, W.wstep * 4);
+    bulk_g2s(smem + (buf ? a.sm.weights2 : a.sm.weights), a.params + (size_t)k * W.wstep, W.wstep * 4, s_mbar_w);
+  };
   if (tma) {
     if (tid == 0) {
       mbar_init(s_mbar, 1);
+      if (tma_w) mbar_init(s_mbar_w, 1);
       fence_proxy_async();
       if ((int)blockIdx.x < a.nbatch && bulk_ok(blockIdx.x)) bulk_issue(blockIdx.x);
+      if (tma_w && (int)blockIdx.x < a.nbatch) weights_issue(0, 0);
     }
     __syncthreads();
   }
@@ -221,18 +233,31 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 
     for (int k = 0; k < K; ++k) {
       // ---------------- stage this step's weights ----------------
-      {
+      if (tma_w) {
+        mbar_wait(s_mbar_w, w_phase);            // this step's weights have landed
+        w_phase ^= 1;
+        s_w = smem + (w_buf ? a.sm.weights2 : a.sm.weights);
+        w_buf ^= 1;
+      } else {
         const float4* src = reinterpret_cast<const float4*>(a.params + (size_t)k * W.wstep);
-        float4* dst = reinterpret_cast<float4*>(s_w);
+        float4* dst = reinterpret_cast<float4*>(smem + a.sm.weights);
         for (int i = tid; i < W.wstep / 4; i += T) dst[i] = __ldg(src + i);
       }
       // ---------------- checkpoint: state entering step k (k >= 1) ----------------
       if (a.need_grad && k >= 1) {
-        const int nst = (4 + L) * NG;
-        float* dstg = a.ckpt + ((size_t)batch * K + (k - 1)) * (size_t)pad4(nst);
-        for (int i = tid; i < nst; i += T) dstg[i] = s_state[i];
+        const int nst4 = (4 + L) * NG / 4;
+        float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (k - 1)) * (size_t)((4 + L) * NG));
+        const float4* srcs = reinterpret_cast<const float4*>(s_state);
+        for (int i = tid; i < nst4; i += T) __stcs(dstg + i, srcs[i]);
       }
       __syncthreads();
+      // Every thread is past the weight wait, and the other buffer was last read before the barrier
+      // that ended the previous step: refill it with the next step's weights.  (Issuing before this
+      // barrier could complete two phases ahead of a slow waiter, which would then spin forever.)
+      if (tma_w && tid == 0 && ((k + 1 < K) || (batch + (int)gridDim.x < a.nbatch))) {
+        fence_proxy_async();
+        weights_issue(k + 1 < K ? k + 1 : 0, w_buf);
+      }
 
       // ---------------- bus phase: phi nets, aggregation, L nets ----------------
       {
@@ -552,9 +577,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 
     // ---------------- outputs ----------------
     if (a.need_grad) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
-      const int nst = (4 + L) * NG;
-      float* dstg = a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)pad4(nst);
-      for (int i = tid; i < nst; i += T) dstg[i] = s_state[i];
+      const int nst4 = (4 + L) * NG / 4;
+      float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)((4 + L) * NG));
+      const float4* srcs = reinterpret_cast<const float4*>(s_state);
+      for (int i = tid; i < nst4; i += T) __stcs(dstg + i, srcs[i]);
     }
     block_sum_per_grid<VG>(loss_tot, s_red, NGQ);
     block_sum_per_grid<VG>(loss_last, s_red, NGQ);

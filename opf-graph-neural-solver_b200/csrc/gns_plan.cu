@@ -44,7 +44,7 @@ static int env_int(const char* name, int dflt) {
 
 static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, int wstep, int nwarps, int topo_u16,
                           int extra_floats, bool backward, int stage_rows_n /* real buses, 0 = no staging */,
-                          int state_rows) {
+                          int state_rows, bool double_weights) {
   SmemPlan s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
@@ -66,6 +66,10 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
     s.stage_l = take(G * E * 7 + 8);
     s.stage_g = take(G * Gn * 7 + 8);
     s.mbar = take(4);
+    if (double_weights) {
+      s.weights2 = take(wstep);
+      s.mbar_w = take(4);
+    }
   }
   s.extra = o;
   o += pad4(extra_floats);
@@ -115,8 +119,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
   const int force_vg = env_int(backward ? "GNS_BWD_VG" : "GNS_FWD_VG", 0);
   const int force_ngq = env_int(backward ? "GNS_BWD_NGQ" : "GNS_FWD_NGQ", 0);
   const int target_threads = env_int("GNS_TARGET_THREADS", 320);
-  bool use_stage = !backward && !env_int("GNS_NO_TMA", 0);
-  for (int pass = 0; pass < 2 && !found; ++pass, use_stage = false)
+  const bool allow_tma = !backward && !env_int("GNS_NO_TMA", 0);
   for (int VG : {2, 1}) {
     if (force_vg && VG != force_vg) continue;
     if (backward && VG != 1) continue;          // the backward kernel handles one grid per thread
@@ -135,10 +138,22 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       g.tmax = (T <= 384) ? 384 : 1024;
       if (g.tmax == 1024 && VG != 1) continue;   // the wide-CTA variant exists for VG=1 only
       const int extra = backward ? backward_extra_floats(N, E, G, md.L, md.H, T) : 0;
-      const SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, use_stage ? plan->N : 0,
-                                      (backward && md.L > 32) ? 4 : 4 + md.L);
-      const size_t bytes = (size_t)sm.total_floats * 4;
+      // TMA extras (input staging, second weight buffer) are taken only while they do not lower the
+      // number of CTAs that fit on one SM (228 KB per SM, 1 KB reserved per CTA)
+      const int state_rows = (backward && md.L > 32) ? 4 : 4 + md.L;
+      const int reg_ctas = std::max(1, 65536 / (T * (g.tmax == 384 ? 168 : 64)));      // register-file limit
+      auto ctas_per_sm = [&](size_t b) { return std::min(reg_ctas, (int)((size_t)233472 / (b + 1024))); };
+      SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, 0, state_rows, false);
+      size_t bytes = (size_t)sm.total_floats * 4;
       if ((int)bytes > limit) continue;
+      if (allow_tma) {
+        for (int level = 2; level >= 1; --level) {
+          const SmemPlan t = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, plan->N,
+                                       state_rows, level == 2);
+          const size_t tb = (size_t)t.total_floats * 4;
+          if ((int)tb <= limit && ctas_per_sm(tb) >= ctas_per_sm(bytes)) { sm = t; bytes = tb; break; }
+        }
+      }
       g.smem_bytes = bytes; g.sm = sm;
       balance_warps(plan, &g);
       g.nbatch = (int)nb; g.num_sms = plan->num_sms;
