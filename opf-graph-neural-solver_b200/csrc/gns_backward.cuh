@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
     if (slot < N) {                                                        // `slot` is an alias LINE id here
       const float r = s_linef[0 * EG + jb], x = s_linef[1 * EG + jb];
       s_y[jb] = 1.0f / sqrtf(r * r + x * x);
+      s_y[NG + jb] = 1.0f / s_linef[3 * EG + jb];           // 1 / tau, like the forward kernel
     }
     for (int it = tid; it < Gn * NGQ; it += T) {
       part4[1] += s_genc[2 * GnG + it];
@@ -361,9 +362,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         const float thf = s_nxt[1 * NG + fi * G + gq], tht = s_nxt[1 * NG + ti * G + gq];
         const float g_pf = s_adj[2 * NG + ti * G + gq];      // p_from lands on the receiving bus
         const float g_pt = s_adj[2 * NG + fi * G + gq];      // p_to lands on the sending bus
-        const float Yf = s_y[fa * G + gq], tauf = s_linef[3 * EG + fa * G + gq], shf = s_linef[4 * EG + fa * G + gq];
+        const float Yf = s_y[fa * G + gq], itf = s_y[NG + fa * G + gq], shf = s_linef[4 * EG + fa * G + gq];
         const float Df = s_trig[0 * NG + fa * G + gq], sDf = s_trig[1 * NG + fa * G + gq], cDf = s_trig[2 * NG + fa * G + gq];
-        const float Yt = s_y[ta * G + gq], taut = s_linef[3 * EG + ta * G + gq], sht = s_linef[4 * EG + ta * G + gq];
+        const float Yt = s_y[ta * G + gq], itt = s_y[NG + ta * G + gq], sht = s_linef[4 * EG + ta * G + gq];
         const float DB = s_trig[0 * NG + ta * G + gq], sDB = s_trig[1 * NG + ta * G + gq], cDB = s_trig[2 * NG + ta * G + gq];
         const float a1 = thf - tht - Df - shf;
         const float a2 = tht - thf - Df + shf;
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         fast_sincos(a1, s1, c1);
         fast_sincos(a2, s2, c2);
         fast_sincos(a3, s3, c3);
-        const float yft = Yf / tauf, yftt = Yf / (tauf * tauf), ytt = Yt / taut;
+        const float yft = Yf * itf, yftt = Yf * (itf * itf), ytt = Yt * itt;
         const float t1 = vf * vt * yft, u1 = vt * vf * ytt;
         const float sDt = -sDB;
         const float ss = s1 + s2;

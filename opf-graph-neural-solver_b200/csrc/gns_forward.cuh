@@ -202,6 +202,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
       for (int g = 0; g < VG; ++g) y[g] = 1.0f / sqrtf(r[g] * r[g] + x[g] * x[g]);
       IO::st(s_y + slot * G + gcol, y);
+      // reciprocal tap ratio once per batch: the per-step flows multiply instead of dividing, which
+      // removes the IEEE-division slow-path branches from the line phase (<= 1 ulp vs x / tau)
+      IO::ld(x, s_linef + 3 * EG + slot * G + gcol);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) y[g] = 1.0f / x[g];
+      IO::st(s_y + NG + slot * G + gcol, y);
     }
     for (int it = tid; it < Gn * NGQ; it += T) {
       const int j = it / NGQ;
@@ -442,6 +448,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       float pj[VG];
 #pragma unroll
       for (int g = 0; g < VG; ++g) pj[g] = 0.f;
+      // two line items of a thread are interleaved (E is just above the thread count on case300: the
+      // second, nearly empty round would otherwise cost a full sincos latency chain)
+#pragma unroll 2
       for (int it = tid; it < E * NGQ; it += T) {
         const int e = it / NGQ;
         const int fi = t_fi[e], ti = t_ti[e], fa = t_fa[e], ta = t_ta[e];
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         float Yf[VG], tauf[VG], shf[VG], bf[VG], Df[VG], sDf[VG], cDf[VG];
         IO::ld(Yf, s_y + fa * G + gcol);
         IO::ld(bf, s_linef + 2 * EG + fa * G + gcol);
-        IO::ld(tauf, s_linef + 3 * EG + fa * G + gcol);
+        IO::ld(tauf, s_y + NG + fa * G + gcol);      // 1 / tau
         IO::ld(shf, s_linef + 4 * EG + fa * G + gcol);
         IO::ld(Df, s_trig + 0 * NG + fa * G + gcol);
         IO::ld(sDf, s_trig + 1 * NG + fa * G + gcol);
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         float Yt[VG], taut[VG], sht[VG], bt[VG], Dt[VG], sDt[VG];
         IO::ld(Yt, s_y + ta * G + gcol);
         IO::ld(bt, s_linef + 2 * EG + ta * G + gcol);
-        IO::ld(taut, s_linef + 3 * EG + ta * G + gcol);
+        IO::ld(taut, s_y + NG + ta * G + gcol);      // 1 / tau
         IO::ld(sht, s_linef + 4 * EG + ta * G + gcol);
         IO::ld(Dt, s_trig + 0 * NG + ta * G + gcol);
         IO::ld(sDt, s_trig + 1 * NG + ta * G + gcol);
@@ -477,14 +486,14 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
           fast_sincos(a2, s2, c2);
           fast_sincos(a3, s3, c3);
           (void)c2;
-          const float t1 = vf[g] * vt[g] * Yf[g] / tauf[g];
-          const float vft = vf[g] / tauf[g];
-          const float msg = fabsf(t1 * (s1 + s2) + (vf[g] / (tauf[g] * tauf[g])) * Yf[g] * sDf[g] +
+          const float t1 = vf[g] * vt[g] * Yf[g] * tauf[g];
+          const float vft = vf[g] * tauf[g];
+          const float msg = fabsf(t1 * (s1 + s2) + (vf[g] * (tauf[g] * tauf[g])) * Yf[g] * sDf[g] +
                                   (vt[g] * vt[g]) * Yf[g] * sDf[g]);
           pj[g] += msg;
           pf[g] = t1 * s1 + (vft * vft) * Yf[g] * sDf[g];
           qf[g] = -t1 * c1 + (vft * vft) * (Yf[g] * cDf[g] - bf[g] / 2.f);
-          const float u1 = vt[g] * vf[g] * Yt[g] / taut[g];
+          const float u1 = vt[g] * vf[g] * Yt[g] * taut[g];
           pt[g] = u1 * s3 + (vt[g] * vt[g]) * Yt[g] * sdt;
           qt[g] = -u1 * c3 + (vt[g] * vt[g]) * (Yt[g] * sdt - bt[g] / 2.f);
         }

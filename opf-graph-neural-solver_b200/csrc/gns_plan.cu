@@ -54,7 +54,7 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
   s.busc = take(4 * NGs);
   s.genc = take(6 * Gn * G);
   s.linef = take(5 * EGs);
-  s.yline = take(NGs);
+  s.yline = take(2 * NGs);       // Y and 1/tau of the alias lines
   s.trig = take(3 * NGs);
   s.flows = take(backward ? 0 : 4 * EGs);   // the backward kernel keeps its own per-line block
   s.gsum = take(4 * G);
