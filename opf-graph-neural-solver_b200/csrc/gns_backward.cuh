@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   float* const am_rows = MG ? a.mscratch + ((size_t)blockIdx.x * 2 + 1) * L * a.NGs : s_adj + 4 * a.NGs;
 
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  int red_parity = 0;
   const int grp = a.grp_of_warp[warp];                 // bus group of this warp (sub-partition balancing)
   const int slot = grp * (32 / NGQ) + lane / NGQ;
   const int gq = lane % NGQ;
@@ -269,10 +270,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       part4[2] += s_genc[1 * GnG + it];
       part4[3] += s_genc[0 * GnG + it];
     }
-    float tmp1[1];
-    tmp1[0] = part4[1]; block_sum_per_grid<1>(tmp1, s_red, NGQ); const float sPset = tmp1[0];
-    tmp1[0] = part4[2]; block_sum_per_grid<1>(tmp1, s_red, NGQ); const float sPmin = tmp1[0];
-    tmp1[0] = part4[3]; block_sum_per_grid<1>(tmp1, s_red, NGQ); const float sPmax = tmp1[0];
+    float sums[3][1] = {{part4[1]}, {part4[2]}, {part4[3]}};
+    block_sum_multi<1, 3>(sums, s_red, NGQ, red_parity);
+    const float sPset = sums[0][0], sPmin = sums[1][0], sPmax = sums[2][0];
 
     // ---------------- adjoint of the outputs; v', theta', dP', dQ' of the final state ----------------
     if (bus_on) {
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         fast_sincos(d, sd, cd);
         s_trig[0 * NG + jb] = d; s_trig[1 * NG + jb] = sd; s_trig[2 * NG + jb] = cd;
       }
-      block_sum_per_grid<1>(part, s_red, NGQ);      // its barriers also publish s_w, s_state, s_trig, gdP
+      block_sum_per_grid<1>(part, s_red, NGQ, red_parity);      // its barrier also publishes s_w, s_state, s_trig, gdP
       const float adj_pg = part[0] / (lo_branch ? 2.f * (sPset - sPmin) : 2.f * (sPmax - sPset));
 
       // ---------------- physics adjoint (b): per-line partials ----------------

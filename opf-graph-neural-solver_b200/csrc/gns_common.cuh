@@ -346,30 +346,51 @@ __device__ __forceinline__ void load_block(const float* __restrict__ src, float*
   }
 }
 
-// Deterministic per-grid block reduction.  Thread `tid` contributes x[VG] for grids
-// (tid % NGQ)*VG .. +VG.  Requires 32 % NGQ == 0 and blockDim.x % 32 == 0.
-// `red` holds nwarps*G floats.  Every thread receives the total of its own grids.
-template <int VG>
-__device__ __forceinline__ void block_sum_per_grid(float (&x)[VG], float* red, int NGQ) {
+// Deterministic per-grid block reduction of NV values at once.  Thread `tid` contributes
+// x[NV][VG] for grids (tid % NGQ)*VG .. +VG.  Requires 32 % NGQ == 0 and blockDim.x % 32 == 0.
+// `red` holds 2 * nwarps * kRedNV * G floats: the two halves alternate (`parity`), so ONE barrier
+// per call is enough - a thread can only re-enter the half it is still being read from after
+// every thread has passed the barrier of the call in between.  Every thread receives the totals
+// of its own grids; the warp partials are added in a fixed order.
+constexpr int kRedNV = 4;
+template <int VG, int NV>
+__device__ __forceinline__ void block_sum_multi(float (&x)[NV][VG], float* red, int NGQ, int& parity) {
+  static_assert(NV <= kRedNV, "too many values");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int G = NGQ * VG;
+  float* buf = red + parity * (nwarps * kRedNV * G);
+  parity ^= 1;
   for (int off = 16; off >= NGQ; off >>= 1) {
 #pragma unroll
-    for (int g = 0; g < VG; ++g) x[g] += __shfl_xor_sync(0xffffffffu, x[g], off);
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int g = 0; g < VG; ++g) x[v][g] += __shfl_xor_sync(0xffffffffu, x[v][g], off);
   }
   if (lane < NGQ) {
 #pragma unroll
-    for (int g = 0; g < VG; ++g) red[warp * G + lane * VG + g] = x[g];
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int g = 0; g < VG; ++g) buf[(warp * kRedNV + v) * G + lane * VG + g] = x[v][g];
   }
   __syncthreads();
   const int gq = lane % NGQ;
 #pragma unroll
-  for (int g = 0; g < VG; ++g) x[g] = 0.f;
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int g = 0; g < VG; ++g) x[v][g] = 0.f;
+#pragma unroll 1
   for (int w = 0; w < nwarps; ++w) {
 #pragma unroll
-    for (int g = 0; g < VG; ++g) x[g] += red[w * G + gq * VG + g];
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int g = 0; g < VG; ++g) x[v][g] += buf[(w * kRedNV + v) * G + gq * VG + g];
   }
-  __syncthreads();
+}
+
+template <int VG>
+__device__ __forceinline__ void block_sum_per_grid(float (&x)[VG], float* red, int NGQ, int& parity) {
+  float (&xv)[1][VG] = reinterpret_cast<float (&)[1][VG]>(x);
+  block_sum_multi<VG, 1>(xv, red, NGQ, parity);
 }
 
 // ---------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
 
   const int tid = threadIdx.x, T = blockDim.x;
+  int red_parity = 0;
   // bus slot (internal order) in bus phases; the warp -> bus-group map balances the 4 sub-partitions
   const int slot = (int)a.grp_of_warp[tid >> 5] * (32 / NGQ) + (tid & 31) / NGQ;
   const int gq = (tid & 31) % NGQ;
@@ -223,10 +224,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       for (int g = 0; g < VG; ++g) part4[3][g] += x[g];
     }
     float sPd[VG], sPset[VG], sPmin[VG], sPmax[VG];
-    block_sum_per_grid<VG>(part4[0], s_red, NGQ);
-    block_sum_per_grid<VG>(part4[1], s_red, NGQ);
-    block_sum_per_grid<VG>(part4[2], s_red, NGQ);
-    block_sum_per_grid<VG>(part4[3], s_red, NGQ);
+    block_sum_multi<VG, 4>(part4, s_red, NGQ, red_parity);
 #pragma unroll
     for (int g = 0; g < VG; ++g) { sPd[g] = part4[0][g]; sPset[g] = part4[1][g]; sPmin[g] = part4[2][g]; sPmax[g] = part4[3][g]; }
     if (tid < NGQ) {  // keep per-grid sums for the backward pass as well
@@ -510,7 +508,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
         for (int g = 0; g < VG; ++g) pj[g] += (v_own[g] * v_own[g]) * Gs[g];
       }
-      block_sum_per_grid<VG>(pj, s_red, NGQ);   // also orders the s_flow writes before the gathers
+      block_sum_per_grid<VG>(pj, s_red, NGQ, red_parity);   // its barrier also orders the s_flow writes before the gathers
 
       // ---------------- physics 3: slack redistribution + per-bus mismatch ----------------
       float lam[VG];
@@ -591,8 +589,14 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       const float4* srcs = reinterpret_cast<const float4*>(s_state);
       for (int i = tid; i < nst4; i += T) __stcs(dstg + i, srcs[i]);
     }
-    block_sum_per_grid<VG>(loss_tot, s_red, NGQ);
-    block_sum_per_grid<VG>(loss_last, s_red, NGQ);
+    {
+      float l2[2][VG];
+#pragma unroll
+      for (int g = 0; g < VG; ++g) { l2[0][g] = loss_tot[g]; l2[1][g] = loss_last[g]; }
+      block_sum_multi<VG, 2>(l2, s_red, NGQ, red_parity);
+#pragma unroll
+      for (int g = 0; g < VG; ++g) { loss_tot[g] = l2[0][g]; loss_last[g] = l2[1][g]; }
+    }
     if (tid < NGQ) {
 #pragma unroll
       for (int g = 0; g < VG; ++g) {

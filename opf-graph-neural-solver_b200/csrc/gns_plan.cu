@@ -58,7 +58,7 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
   s.trig = take(3 * NGs);
   s.flows = take(backward ? 0 : 4 * EGs);   // the backward kernel keeps its own per-line block
   s.gsum = take(4 * G);
-  s.red = take(nwarps * G);
+  s.red = take(2 * nwarps * kRedNV * G);   // two alternating halves, kRedNV values per warp and grid
   s.weights = take(wstep);
   s.topo = take((topo_u16 + 1) / 2);
   if (!backward && stage_rows_n > 0) {   // raw staging of the next batch's rows (+ slack for the 16-byte window)
