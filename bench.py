@@ -89,6 +89,31 @@ def cpu_reference_run(case, K, L, sample, train, workers):
     return sum(r[0] for r in res) / wall, wall, len(jobs), label
 
 
+def _nr_worker(job):
+    from oracle import newton_raphson as nr
+    tables, idx = job
+    t0 = time.perf_counter()
+    res = nr.newton_pf_batch(tables, idx)
+    return len(idx), sum(r[2] for r in res), time.perf_counter() - t0
+
+
+def nr_baseline(case, sample, workers):
+    """Restated Newton-Raphson (not pypower, which is not installable offline) on the same
+    synthetic samples, one single-threaded worker per host core (ref GNS/evaluate.py:31-40)."""
+    import multiprocessing as mp
+    import opf_graph_neural_solver_b200 as pkg
+    tables = pkg.data.augment(pkg.data.get_case(case)[0], sample, seed=1)
+    workers = max(1, min(workers, sample))
+    chunks = [list(range(i, sample, workers)) for i in range(workers)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = pool.map(_nr_worker, [(tables, c) for c in chunks])
+    wall = time.perf_counter() - t0
+    n, conv = sum(r[0] for r in res), sum(r[1] for r in res)
+    return {"value": n / wall, "unit": "grids/s", "cores": workers, "kind": "restated NR, not pypower",
+            "sample": f"{n} grids, tol 1e-8, max 10 iterations, flat start", "converged": conv}
+
+
 def run_reference_arm(args):
     """`--impl reference`: rank 0 only; other ranks exit 0 without work."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -119,6 +144,10 @@ def run_reference_arm(args):
         "e2e": {"value": gps, "unit": "grids/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["cpu_baseline"]["newton_raphson"] = nr_baseline(args.case, min(sample, max(workers * 2, 32)), workers)
+    except Exception as ex:  # pragma: no cover
+        line["cpu_baseline"]["newton_raphson"] = {"value": None, "error": str(ex)}
     print(json.dumps(line), flush=True)
 
 

@@ -13,8 +13,8 @@ module raises at call time.
 """
 from .model import GNS, LearningBlock, get_BLG            # noqa: F401
 from .plan import TopologyPlan                            # noqa: F401
-from . import data, parallel                              # noqa: F401
+from . import data, parallel, train                       # noqa: F401
 from ._lib import load_library, library_path, build_library  # noqa: F401
 
-__all__ = ["GNS", "LearningBlock", "get_BLG", "TopologyPlan", "data", "parallel",
+__all__ = ["GNS", "LearningBlock", "get_BLG", "TopologyPlan", "data", "parallel", "train",
            "load_library", "library_path", "build_library"]

@@ -142,3 +142,23 @@ def test_adam_step_matches_torch(lib):
         g = g * 0.5 + 0.1
     torch.cuda.synchronize()
     assert (p - ref.detach()).abs().max() < 1e-6
+
+
+def test_flat_adam_training_follows_torch_adam(lib):
+    """ref GNS/main.py:243,284-291: three Adam steps on the batch-mean loss, fused flat Adam vs torch.optim.Adam."""
+    buses, lines, gens, _ = pkg.data.make_batch(14, 64, seed=11)
+    b, l, g = buses.cuda(), lines.cuda(), gens.cuda()
+    torch.manual_seed(0)
+    m1 = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    torch.manual_seed(0)
+    m2 = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    o1 = pkg.train.FlatAdam(m1, lr=1e-3)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    for _ in range(3):
+        o1.zero_grad(); m1(b, l, g)[2].mean().backward(); o1.step()
+        o2.zero_grad(); m2(b, l, g)[2].mean().backward(); o2.step()
+    for (n, p1), p2 in zip(m1.named_parameters(), m2.parameters()):
+        assert (p1 - p2).abs().max() < 2e-6, n
+    hist = pkg.train.fit(m1, b, l, g, epochs=3, batch_size=32, log=lambda *_: None)
+    assert len(hist) == 3 and all(h == h for h in hist)
+    assert pkg.train.checkpoint_name(14, m1) == "best_model_c14_K4_L20_H10_True_optimAdam.pth"

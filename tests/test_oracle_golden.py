@@ -59,3 +59,16 @@ def test_dq_is_cancellation_noise():
     m, theta, v, dP, dQ = orc.init_state(g["buses"], g["gens"], gb, g["latent_dim"])
     dP, dQ, *_ = orc.physics(v, theta, g["buses"], g["lines"], g["gens"], f, t, gb)
     assert float(dQ.abs().max()) < 1e-5 and float(dP.abs().max()) > 1e-2
+
+
+def test_newton_raphson_restatement_reproduces_ieee14_solution():
+    """Known answer of the IEEE 14-bus case (MATPOWER/pypower case14 solution): the restated NR is
+    only a reported CPU baseline (ref GNS/evaluate.py:31-40), but it should still be a power flow."""
+    import opf_graph_neural_solver_b200 as pkg
+    from oracle import newton_raphson as nr
+    vm, va, ok, it = nr.newton_pf(pkg.data.case14())
+    assert ok and it <= 5
+    deg = np.degrees(va)
+    assert abs(vm[13] - 1.0355) < 2e-4 and abs(deg[13] + 16.03) < 0.01      # bus 14
+    assert abs(deg[1] + 4.98) < 0.01 and abs(deg[2] + 12.73) < 0.01          # buses 2, 3
+    assert abs(vm[3] - 1.0177) < 2e-4 and abs(vm[8] - 1.0559) < 2e-4         # buses 4, 9
