@@ -23,7 +23,10 @@ static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStrea
 
 template <int L, int H>
 static FwdLauncher pick_forward(int multi, int VG, int tmax) {
-  if (tmax == 384) {
+  if (tmax == 320) {
+    if (VG == 2) return multi ? launch_forward<L, H, true, 2, 320> : launch_forward<L, H, false, 2, 320>;
+    if (VG == 1) return multi ? launch_forward<L, H, true, 1, 320> : launch_forward<L, H, false, 1, 320>;
+  } else if (tmax == 384) {
     if (VG == 2) return multi ? launch_forward<L, H, true, 2, 384> : launch_forward<L, H, false, 2, 384>;
     if (VG == 1) return multi ? launch_forward<L, H, true, 1, 384> : launch_forward<L, H, false, 1, 384>;
   } else if (tmax == 1024 && VG == 1) {
@@ -50,6 +53,7 @@ static cudaError_t launch_backward(const BwdArgs& a, const Geometry& g, cudaStre
 
 template <int L, int H>
 static BwdLauncher pick_backward(int multi, int tmax) {
+  if (tmax == 320) return multi ? launch_backward<L, H, true, 320> : launch_backward<L, H, false, 320>;
   if (tmax == 384) return multi ? launch_backward<L, H, true, 384> : launch_backward<L, H, false, 384>;
   if (tmax == 1024) return multi ? launch_backward<L, H, true, 1024> : launch_backward<L, H, false, 1024>;
   return nullptr;

@@ -135,13 +135,13 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
       if (!force_ngq && NGQ > 1 && (T > std::max(target_threads, 32) || nb < 2LL * plan->num_sms)) continue;
       Geometry g{};
       g.VG = VG; g.NGQ = NGQ; g.G = G; g.T = T;
-      g.tmax = (T <= 384) ? 384 : 1024;
+      g.tmax = (T <= 320) ? 320 : ((T <= 384) ? 384 : 1024);   // launch-bounds variant (registers per thread)
       if (g.tmax == 1024 && VG != 1) continue;   // the wide-CTA variant exists for VG=1 only
       const int extra = backward ? backward_extra_floats(N, E, G, md.L, md.H, T) : 0;
       // TMA extras (input staging, second weight buffer) are taken only while they do not lower the
       // number of CTAs that fit on one SM (228 KB per SM, 1 KB reserved per CTA)
       const int state_rows = (backward && md.L > 32) ? 4 : 4 + md.L;
-      const int reg_ctas = std::max(1, 65536 / (T * (g.tmax == 384 ? 168 : 64)));      // register-file limit
+      const int reg_ctas = std::max(1, 65536 / (T * (g.tmax == 320 ? 200 : (g.tmax == 384 ? 168 : 64))));      // register-file limit
       auto ctas_per_sm = [&](size_t b) { return std::min(reg_ctas, (int)((size_t)233472 / (b + 1024))); };
       SmemPlan sm = plan_smem(N, E, Gn, G, md.L, W.wstep, T / 32, plan->to.total, extra, backward, 0, state_rows, false);
       size_t bytes = (size_t)sm.total_floats * 4;
@@ -307,7 +307,7 @@ extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* 
   for (int s = 0; s < n_bus; ++s) p->bus_rank[p->bus_order[s]] = s;
 
   // ---- slots: a bus with more than deg_cap incoming lines is split over 2 or 4 adjacent slots ----
-  p->deg_cap = std::max(1, env_int("GNS_DEG_CAP", 2));
+  p->deg_cap = std::max(1, env_int("GNS_DEG_CAP", 3));   // measured best on case300 (2: 3.62, 3: 3.68, 4: 3.51 M grids/s)
   const int max_group = std::max(1, std::min(4, env_int("GNS_MAX_TWINS", 4)));
   auto group_size = [&](int deg) {
     int need = (deg + p->deg_cap - 1) / p->deg_cap, g = 1;

@@ -175,7 +175,8 @@ def test_slot_tables_split_high_degree_buses_consistently(lib, n_bus):
         assert (sb[pos:pos + g] == b).all() and (sp[pos:pos + g] == pos).all() and (gs[pos:pos + g] == g).all()
         assert b0[pos] == covered and b1[pos + g - 1] == covered + deg[b]
         assert (b0[pos + 1:pos + g] == b1[pos:pos + g - 1]).all()        # consecutive sub-ranges
-        assert (b1[pos:pos + g] - b0[pos:pos + g]).max() <= max(2, -(-deg[b] // 4))
+        assert (b1[pos:pos + g] - b0[pos:pos + g]).max() == -(-deg[b] // g)      # even split
+        assert g == min(4, 1 << max(0, int(np.ceil(np.log2(max(1, -(-deg[b] // 3)))))))   # cap of 3 lines per slot, <= 4 twins
         covered += deg[b]
         pos += g
     assert pos == len(sb) and covered == len(t)
