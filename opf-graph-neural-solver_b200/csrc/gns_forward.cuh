@@ -269,6 +269,14 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         float* st = s_state + n * G + gcol;
         const float* sm_m = st + 4 * NG;
         const float degf = (float)(e_full1 - e_in0); // in-degree of the bus (primary)
+        // the bus's latent is read by six matrix-vector products per step (3 phi + 3 L nets): keep it
+        // in registers when it is small enough (L*VG <= 40), else re-read it from shared memory
+        constexpr bool MREG = (L * VG <= 40);
+        float mreg[MREG ? L : 1][VG];
+        if constexpr (MREG) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) IO::ld(mreg[i], sm_m + i * NG);
+        }
         float st4[4][VG];
 #pragma unroll
         for (int q = 0; q < 4; ++q) IO::ld(st4[q], st + q * NG);
@@ -292,11 +300,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
                 for (int g = 0; g < VG; ++g) P[o][g] = b[o];
             }
+            if constexpr (MREG) {
+#pragma unroll
+              for (int i = 0; i < L; ++i) row_axpy<H, HP, VG>(P, mreg[i], wphi + W.phi_w1m + i * HP);
+            } else {
 #pragma unroll 4
-            for (int i = 0; i < L; ++i) {
-              float x[VG];
-              IO::ld(x, sm_m + i * NG);
-              row_axpy<H, HP, VG>(P, x, wphi + W.phi_w1m + i * HP);
+              for (int i = 0; i < L; ++i) {
+                float x[VG];
+                IO::ld(x, sm_m + i * NG);
+                row_axpy<H, HP, VG>(P, x, wphi + W.phi_w1m + i * HP);
+              }
             }
             for (int e = e_in0; e < e_in1; ++e) {
               const float* lf = s_linef + (int)t_ini[e] * G + gcol;
@@ -355,11 +368,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) row_axpy<H, HP, VG>(zL, st4[i], wln + W.ln_w1 + i * HP);
+          if constexpr (MREG) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) row_axpy<H, HP, VG>(zL, mreg[i], wln + W.ln_w1 + (4 + i) * HP);
+          } else {
 #pragma unroll 4
-          for (int i = 0; i < L; ++i) {
-            float x[VG];
-            IO::ld(x, sm_m + i * NG);
-            row_axpy<H, HP, VG>(zL, x, wln + W.ln_w1 + (4 + i) * HP);
+            for (int i = 0; i < L; ++i) {
+              float x[VG];
+              IO::ld(x, sm_m + i * NG);
+              row_axpy<H, HP, VG>(zL, x, wln + W.ln_w1 + (4 + i) * HP);
+            }
           }
           {   // S = W4 A + deg b4 feeds the first layer linearly: use the pre-multiplied block
               // M = W4^T W1[:, 4+L:]^T and c = b4 W1[:, 4+L:]^T (fuse_params_kernel): H*H instead of 2*L*H MACs
