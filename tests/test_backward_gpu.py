@@ -168,3 +168,29 @@ def test_flat_adam_training_follows_torch_adam(lib):
     hist = pkg.train.fit(m1, b, l, g, epochs=3, batch_size=32, log=lambda *_: None)
     assert len(hist) == 3 and all(h == h for h in hist)
     assert pkg.train.checkpoint_name(14, m1) == "best_model_c14_K4_L20_H10_True_optimAdam.pth"
+
+
+def test_large_grid_gradients_wide_cta_variant(lib):
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=10, hidden_dim=10, K=2, gamma=0.9, multiple_phi=True).cuda()
+    case = pkg.data.synthetic_case(400, 520, 50, seed=2)     # > 384 slots: 1024-thread variant, still fits shared memory
+    aug = pkg.data.augment(case, 3, seed=1)
+    buses, lines, gens = pkg.data.pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    (_, _, otot, _), want = orc.gns_loss_and_grads(params, buses.double(), lines.double(), gens.double(), K=2,
+                                                   latent_dim=10, gamma=0.9, multiple_phi=True)
+    out = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    out[2].mean().backward()
+    assert_loss_close(out[2], otot, "total")
+    assert_grads_close(_grads(model), want, "400-bus grid")
+    assert model._last_plan.launch_info(3, 2, 10, 10, True, backward=True)["tmax"] == 1024
+
+
+def test_backward_refuses_grids_that_do_not_fit_shared_memory(lib):
+    """No silent fallback: a 700-bus grid trains nowhere else, so the call must raise."""
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=2, multiple_phi=True).cuda()
+    case = pkg.data.synthetic_case(700, 900, 80, seed=2)
+    aug = pkg.data.augment(case, 2, seed=1)
+    buses, lines, gens = pkg.data.pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
+    with pytest.raises(RuntimeError, match="no launch geometry fits"):
+        model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)

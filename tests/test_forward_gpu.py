@@ -138,3 +138,28 @@ def test_infer_host_streams_chunks_and_matches_forward(lib):
     got = model.infer_host(buses.pin_memory(), lines.pin_memory(), gens.pin_memory(), chunk=192)   # ragged last chunk
     for g, w in zip(got, want):   # chunks may pick another launch geometry: same math, other summation order
         assert g.device.type == "cpu" and torch.allclose(g, w.cpu(), rtol=1e-5, atol=1e-6)
+
+
+def test_reference_default_constructor_k30(lib):
+    """GNS() defaults of the reference (latent 10, hidden 10, K=30, single phi).  At random init the
+    30-step recurrence is ill-conditioned, so the weights are damped to keep the
+    float32/float64 comparison meaningful."""
+    torch.manual_seed(0)
+    model = pkg.GNS().cuda()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(0.5)
+    buses, lines, gens, _ = pkg.data.make_batch(14, 9, seed=8)
+    _check_against_oracle(model, buses, lines, gens, "defaults K=30")
+
+
+def test_large_grid_uses_the_wide_cta_variant(lib):
+    """700 buses / 900 lines: more than 384 threads per grid -> the 1024-thread kernel variant."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=10, hidden_dim=10, K=2, gamma=0.9, multiple_phi=True).cuda()
+    case = pkg.data.synthetic_case(700, 900, 80, seed=2)
+    aug = pkg.data.augment(case, 5, seed=1)
+    buses, lines, gens = pkg.data.pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
+    _check_against_oracle(model, buses, lines, gens, "700-bus grid")
+    info = model._last_plan.launch_info(5, 2, 10, 10, True)
+    assert info["threads"] > 384 and info["tmax"] == 1024
