@@ -420,6 +420,21 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       // adjv / adjth now hold d loss / d v', d theta' of this thread's bus (registers).
 
       // ---------------- MLP adjoint + weight gradients (bus-centric, warp tiles) ----------------
+      {   // pull what the next step (or the next batch) loads first towards L2 while this phase computes
+        if (k >= 2) {
+          const char* nx = reinterpret_cast<const char*>(a.ckpt + ((size_t)bf * K + (k - 2)) * ck_stride);
+          for (int i = tid * 128; i < (int)(ck_stride * 4); i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+        } else if (k == 0 && batch + (int)gridDim.x < a.nbatch) {
+          const long long gn = (long long)(batch + gridDim.x) * G;
+          const char* pb = reinterpret_cast<const char*>(a.buses + gn * N * 6);
+          const char* pl = reinterpret_cast<const char*>(a.lines + gn * E * 7);
+          for (int i = tid * 128; i < G * N * 24; i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
+          for (int i = tid * 128; i < G * E * 28; i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + i));
+          const long long bfn = ((gn < a.S ? gn : a.S - 1)) / a.Gf;
+          const char* nx = reinterpret_cast<const char*>(a.ckpt + ((size_t)bfn * K + (K - 2 >= 0 ? K - 2 : 0)) * ck_stride);
+          for (int i = tid * 128; i < (int)(ck_stride * 4); i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+        }
+      }
       float* const gk = gacc_w + (size_t)k * W.wstep;
       {
         const float* st = s_state + nb;
