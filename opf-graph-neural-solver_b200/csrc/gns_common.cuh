@@ -307,20 +307,18 @@ __device__ __forceinline__ BulkWindow bulk_window(long long first, int count) {
   return w;
 }
 
-// same de-interleave as load_block, but from the staged raw rows in shared memory
+// same de-interleave as load_block, but from the staged raw rows in shared memory; one thread per
+// (grid, row): one integer division per row instead of two per element
 __device__ __forceinline__ void unpack_block(const float* __restrict__ raw, float* __restrict__ dst, int G, int rows,
                                              int cols, int c0, int dst_stride, const uint16_t* __restrict__ slot_of_row) {
-  const int per_grid = rows * cols;
-  const int total = per_grid * G;
+  const int total = rows * G;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int gl = idx / per_grid;
-    const int rem = idx - gl * per_grid;
-    const int row = rem / cols;
-    const int c = rem - row * cols;
-    if (c >= c0) {
-      const int slot = slot_of_row ? (int)slot_of_row[row] : row;
-      dst[(c - c0) * dst_stride + slot * G + gl] = raw[idx];
-    }
+    const int gl = idx / rows;
+    const int row = idx - gl * rows;
+    const int slot = slot_of_row ? (int)slot_of_row[row] : row;
+    const float* src = raw + idx * cols;
+    float* d = dst + slot * G + gl;
+    for (int c = c0; c < cols; ++c) d[(c - c0) * dst_stride] = src[c];
   }
 }
 
