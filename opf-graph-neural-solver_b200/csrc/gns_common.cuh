@@ -327,20 +327,21 @@ __device__ __forceinline__ void unpack_block(const float* __restrict__ raw, floa
 __device__ __forceinline__ void load_block(const float* __restrict__ src, float* __restrict__ dst,
                                            long long g0, long long S, int G, int rows, int cols, int c0,
                                            int dst_stride, const uint16_t* __restrict__ slot_of_row) {
-  const int per_grid = rows * cols;
-  const int total = per_grid * G;
+  const int total = rows * G;                 // one thread per (grid, row): its columns are independent loads
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int gl = idx / per_grid;
-    const int rem = idx - gl * per_grid;
-    const int row = rem / cols;
-    const int c = rem - row * cols;
+    const int gl = idx / rows;
+    const int row = idx - gl * rows;
     long long g = g0 + gl;
     if (g >= S) g = S - 1;  // tail batch: replicate the last grid (results are not stored)
-    const float val = __ldg(src + g * per_grid + rem);
-    if (c >= c0) {
-      const int slot = slot_of_row ? (int)slot_of_row[row] : row;
-      dst[(c - c0) * dst_stride + slot * G + gl] = val;
-    }
+    const float* s = src + (g * rows + row) * cols;
+    const int slot = slot_of_row ? (int)slot_of_row[row] : row;
+    float* d = dst + slot * G + gl;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = (c >= c0 && c < cols) ? __ldg(s + c) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c >= c0 && c < cols) d[(c - c0) * dst_stride] = v[c];
   }
 }
 
