@@ -46,33 +46,38 @@ class LearningBlock(nn.Module):
         raise RuntimeError("LearningBlock is evaluated inside the fused GNS kernels; call GNS.forward")
 
 
+def _run_forward(module, plan, need_grad, buses, lines, gens, flat):
+    """One ``gns_forward`` call on device tensors; returns (v, theta, total, last, workspace)."""
+    lib = _lib.load_library()
+    S, N = buses.shape[0], buses.shape[1]
+    dev = buses.device
+    K, Ld, Hd, multi = module.K, module.latent_dim, module.hidden_dim, int(module.multiple_phis)
+    nbytes = lib.gns_workspace_bytes(plan.handle, S, K, Ld, Hd, multi, int(need_grad))
+    if nbytes < 0:
+        raise RuntimeError("gns_workspace_bytes: " + _lib.last_error())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(2 * S * N + 2 * S, dtype=torch.float32, device=dev)      # one allocation for the four outputs
+    v, theta = out[:S * N].view(S, N), out[S * N:2 * S * N].view(S, N)
+    total, last = out[2 * S * N:2 * S * N + S], out[2 * S * N + S:]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.gns_forward(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
+                         S, K, Ld, Hd, multi, float(module.gamma),
+                         v.data_ptr(), theta.data_ptr(), total.data_ptr(), last.data_ptr(),
+                         ws.data_ptr(), nbytes, int(need_grad), stream)
+    _lib.check(rc, "gns_forward")
+    return v, theta, total, last, ws
+
+
 class _GNSFunction(torch.autograd.Function):
     """autograd glue: one ``gns_forward`` / one ``gns_backward`` call per step."""
 
     @staticmethod
     def forward(ctx, module, plan, need_grad, buses, lines, gens, flat, *params):
-        lib = _lib.load_library()
-        S, N = buses.shape[0], buses.shape[1]
-        dev = buses.device
-        K, Ld, Hd, multi = module.K, module.latent_dim, module.hidden_dim, int(module.multiple_phis)
-        nbytes = lib.gns_workspace_bytes(plan.handle, S, K, Ld, Hd, multi, int(need_grad))
-        if nbytes < 0:
-            raise RuntimeError("gns_workspace_bytes: " + _lib.last_error())
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        v = torch.empty(S, N, dtype=torch.float32, device=dev)
-        theta = torch.empty(S, N, dtype=torch.float32, device=dev)
-        total = torch.empty(S, dtype=torch.float32, device=dev)
-        last = torch.empty(S, dtype=torch.float32, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.gns_forward(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
-                             S, K, Ld, Hd, multi, float(module.gamma),
-                             v.data_ptr(), theta.data_ptr(), total.data_ptr(), last.data_ptr(),
-                             ws.data_ptr(), nbytes, int(need_grad), stream)
-        _lib.check(rc, "gns_forward")
+        v, theta, total, last, ws = _run_forward(module, plan, need_grad, buses, lines, gens, flat)
         if need_grad:
             ctx.module, ctx.plan, ctx.ws = module, plan, ws
             ctx.save_for_backward(buses, lines, gens, flat, v)
-            ctx.shapes = [p.shape for p in params]
+            ctx.shapes = [p.shape for p in params]     # empty in flat-leaf mode
         return v, theta, total, last
 
     @staticmethod
@@ -101,11 +106,19 @@ class _GNSFunction(torch.autograd.Function):
                               keep[0].data_ptr(), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
                               grad_flat.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "gns_backward")
-        grads, off = [], 0
+        if not ctx.shapes:      # flat-leaf mode: one gradient for the flat parameter buffer
+            return (None, None, None, None, None, None, grad_flat)
+        # Per-parameter gradients alias ONE flat buffer (a single all-reduce / fused Adam can use it), but
+        # are handed to autograd as storage aliases rather than views: AccumulateGrad clones view
+        # gradients, which cost one tiny copy kernel per parameter tensor (144 of them for K=4).
+        grads, off, storage = [], 0, grad_flat.untyped_storage()
+        base = grad_flat.storage_offset()
         for shp in ctx.shapes:
             n = shp.numel()
-            grads.append(grad_flat[off:off + n].view(shp))
+            g = torch.empty(0, dtype=torch.float32, device=dev).set_(storage, base + off, shp)
+            grads.append(g)
             off += n
+        module._last_grad_flat = grad_flat
         return (None, None, None, None, None, None, None) + tuple(grads)
 
 
@@ -141,6 +154,17 @@ class GNS(nn.Module):
         # --- not part of the reference surface ---
         self.validate_topology = True     # device-side check that a batch shares the plan's topology
         self._flat = None                 # flat float32 parameter storage, state_dict order
+        self._param_list = None
+        self._last_grad_flat = None       # flat gradient buffer of the most recent backward
+        # Gradient delivery.  Default: ONE autograd leaf (the flat buffer); a post-accumulate hook then
+        # exposes the result as per-parameter ``.grad`` aliases of one persistent flat gradient buffer.
+        # A reference-style loop (128 forward calls, one backward, ref GNS/main.py:279-288) otherwise
+        # pays 144 AccumulateGrad nodes per call.  Set True to put every Parameter into the autograd
+        # graph instead (needed for per-parameter hooks, torch.autograd.grad w.r.t. parameters, DDP).
+        self.per_parameter_autograd = False
+        self._flat_leaf = None
+        self._grad_flat = None
+        self._grad_aliases = None
         self._plans = {}                  # topology key -> TopologyPlan
         self._last_plan = None
 
@@ -149,13 +173,14 @@ class GNS(nn.Module):
         f = self._flat
         if f is None:
             return False
+        if self._param_list is None:
+            self._param_list = [(p, p.numel()) for p in self.parameters()]
         base, off = f.data_ptr(), 0
-        for p in self.parameters():
-            if p.device != f.device or p.dtype != torch.float32 or p.data_ptr() != base + 4 * off \
-                    or not p.is_contiguous():
+        for p, n in self._param_list:      # a parameter that moved (.to / .cuda / re-assignment) has another address
+            if p.data_ptr() != base + 4 * off:
                 return False
-            off += p.numel()
-        return off == f.numel()
+            off += n
+        return off == f.numel() and self._param_list[0][0].device == f.device
 
     def flatten_parameters(self):
         """Re-home every parameter as a view of one flat float32 buffer in ``state_dict`` order
@@ -171,6 +196,8 @@ class GNS(nn.Module):
                 p.data = flat[off:off + n].view(p.shape)
                 off += n
         self._flat = flat
+        self._param_list = [(p, p.numel()) for p in params]
+        self._flat_leaf = self._grad_flat = self._grad_aliases = None
         assert flat.device == dev
         return flat
 
@@ -178,6 +205,38 @@ class GNS(nn.Module):
         if not self._flat_ok():
             self.flatten_parameters()
         return self._flat
+
+    def _leaf(self) -> torch.Tensor:
+        """The flat buffer as the single autograd leaf of the fast gradient path."""
+        if self._flat_leaf is None:
+            leaf = self._flat.detach().requires_grad_(True)      # shares storage with the parameters
+            leaf.register_post_accumulate_grad_hook(self._deliver_gradients)
+            self._flat_leaf = leaf
+        return self._flat_leaf
+
+    def _deliver_gradients(self, leaf):
+        g, leaf.grad = leaf.grad, None
+        params = self._param_list
+        if self._grad_flat is None:
+            self._grad_flat = torch.empty_like(g)
+            storage, off, aliases = self._grad_flat.untyped_storage(), 0, []
+            for p, n in params:
+                aliases.append(torch.empty(0, dtype=torch.float32, device=g.device).set_(storage, off, p.shape))
+                off += n
+            self._grad_aliases = aliases
+        fresh = True
+        for (p, _), alias in zip(params, self._grad_aliases):
+            if p.grad is not None and p.grad.data_ptr() == alias.data_ptr():
+                fresh = False
+                break
+        if fresh:
+            self._grad_flat.copy_(g)
+        else:
+            self._grad_flat.add_(g)
+        for (p, _), alias in zip(params, self._grad_aliases):
+            if p.requires_grad and p.grad is None:
+                p.grad = alias
+        self._last_grad_flat = self._grad_flat
 
     # ------------------------------------------------------------------ topology plans
     def plan_for(self, lines: torch.Tensor, generators: torch.Tensor, n_bus: int) -> TopologyPlan:
@@ -225,7 +284,6 @@ class GNS(nn.Module):
             start = torch.cuda.Event(); start.record(comp)
             h2d.wait_event(start)
             flat = self.flat_parameters()
-            params = list(self.parameters())
             plan = None
             for i, a in enumerate(range(0, S, chunk)):
                 b = min(S, a + chunk)
@@ -240,7 +298,7 @@ class GNS(nn.Module):
                 d = [t[:b - a] for t in dbuf[slot]]
                 if plan is None:
                     plan = self.plan_for(d[1], d[2], N)
-                res = _GNSFunction.apply(self, plan, False, d[0], d[1], d[2], flat, *params)
+                res = _run_forward(self, plan, False, d[0], d[1], d[2], flat)[:4]
                 free[slot].record(comp)
                 done = torch.cuda.Event(); done.record(comp)
                 d2h.wait_event(done)
@@ -281,9 +339,14 @@ class GNS(nn.Module):
         with torch.cuda.device(dev):
             flat = self.flat_parameters()
             plan = self.plan_for(lines_d, gens_d, buses_d.shape[1])
-            params = list(self.parameters())
+            params = [p for p, _ in self._param_list]
             need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-            v, theta, total, last = _GNSFunction.apply(self, plan, need_grad, buses_d, lines_d, gens_d, flat, *params)
+            if need_grad and not self.per_parameter_autograd:
+                v, theta, total, last = _GNSFunction.apply(self, plan, True, buses_d, lines_d, gens_d, self._leaf())
+            elif need_grad:
+                v, theta, total, last = _GNSFunction.apply(self, plan, True, buses_d, lines_d, gens_d, flat, *params)
+            else:   # inference: no autograd bookkeeping at all
+                v, theta, total, last, _ = _run_forward(self, plan, False, buses_d, lines_d, gens_d, flat)
         if in_dev != dev:
             v, theta, total, last = (t.to(in_dev) for t in (v, theta, total, last))
         if single:

@@ -15,20 +15,24 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 def flat_gradient(params):
-    """The single buffer behind all parameter gradients when they are views of one flat
-    tensor (what GNS.backward produces), else None."""
+    """One tensor aliasing all parameter gradients when they sit back to back in one storage (what
+    GNS.backward produces), else None."""
     params = [p for p in params if p.grad is not None]
     if not params:
         return None
-    base = params[0].grad._base
-    if base is None:
+    g0 = params[0].grad
+    if g0.dtype != torch.float32 or not g0.is_contiguous():
         return None
-    n = 0
+    ptr, n = g0.data_ptr(), 0
     for p in params:
-        if p.grad._base is not base:
+        g = p.grad
+        if g.data_ptr() != ptr + 4 * n or not g.is_contiguous() or g.dtype != torch.float32:
             return None
-        n += p.grad.numel()
-    return base if n == base.numel() else None
+        n += g.numel()
+    storage = g0.untyped_storage()
+    if (g0.storage_offset() + n) * 4 > storage.nbytes():
+        return None
+    return torch.empty(0, dtype=torch.float32, device=g0.device).set_(storage, g0.storage_offset(), (n,))
 
 
 def allreduce_gradients(params, group=None, average: bool = False):

@@ -194,3 +194,27 @@ def test_backward_refuses_grids_that_do_not_fit_shared_memory(lib):
     buses, lines, gens = pkg.data.pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
     with pytest.raises(RuntimeError, match="no launch geometry fits"):
         model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+
+
+def test_flat_leaf_and_per_parameter_autograd_agree(lib):
+    """Default gradient delivery (one flat autograd leaf + hook) vs every Parameter in the graph."""
+    g = load_golden([p for p in golden_files() if p.endswith("k4_l20_multi.npz")][0])
+    b, l, ge = g["buses"][:6].cuda(), g["lines"][:6].cuda(), g["gens"][:6].cuda()
+    m1 = _model_from(g["params"], 20, 10, 4, 0.9, True)
+    m2 = _model_from(g["params"], 20, 10, 4, 0.9, True)
+    m2.per_parameter_autograd = True
+    for m in (m1, m2):
+        m(b, l, ge, *BLG)[2].mean().backward()
+        m(b[:3], l[:3], ge[:3], *BLG)[2].sum().backward()          # second backward accumulates
+    for (n, p1), p2 in zip(m1.named_parameters(), m2.parameters()):
+        assert torch.allclose(p1.grad, p2.grad, rtol=1e-6, atol=1e-7), n
+    flat = pkg.parallel.flat_gradient(list(m1.parameters()))
+    assert flat is not None and flat.numel() == 14768               # one buffer behind all .grad tensors
+    m1.zero_grad(set_to_none=True)
+    m1(b, l, ge, *BLG)[2].mean().backward()                           # fresh after zero_grad: overwrite, not add
+    m2.zero_grad(set_to_none=True)
+    m2(b, l, ge, *BLG)[2].mean().backward()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(p1.grad, p2.grad, rtol=1e-6, atol=1e-7)
+    grads = torch.autograd.grad(m2(b, l, ge, *BLG)[2].mean(), list(m2.parameters()), allow_unused=True)
+    assert grads[0] is not None                                       # parameters are graph inputs in this mode
