@@ -143,8 +143,13 @@ __device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict
   constexpr int FULL = (R / 32) * 32, REM = R - FULL;
   if (FULL > 0) tile_gemm_chunk<C, 1>(0, FULL, rowfn, hid, g, outfn);
   if (REM > 0) {
-    constexpr int P = GNS_TG_SPLIT ? (REM <= 8 ? 4 : (REM <= 16 ? 2 : 1)) : 1;
-    tile_gemm_chunk<C, P>(FULL, R, rowfn, hid, g, outfn);
+    if (GNS_TG_SPLIT && REM > 16 && REM <= 24) {          // 17..24 rows: 16 rows two-way + the rest four-way
+      tile_gemm_chunk<C, 2>(FULL, FULL + 16, rowfn, hid, g, outfn);
+      tile_gemm_chunk<C, 4>(FULL + 16, R, rowfn, hid, g, outfn);
+    } else {
+      constexpr int P = GNS_TG_SPLIT ? (REM <= 8 ? 4 : (REM <= 16 ? 2 : 1)) : 1;
+      tile_gemm_chunk<C, P>(FULL, R, rowfn, hid, g, outfn);
+    }
   }
 }
 
