@@ -151,6 +151,85 @@ def pack_grids(bus, branch, gen, base_mva: float):
     return buses, lines, generators
 
 
+def renumber_buses(case: dict):
+    """Map arbitrary external bus numbers (e.g. the real IEEE-300 table goes up to 9533) to the
+    contiguous 1..N the path requires; the reference has no such step and raises IndexError at
+    ``m[dst]`` (ref GNS/main.py:153, quirk Q8).  Returns (new case, external ids in internal order)."""
+    bus = np.array(case["bus"], dtype=np.float64, copy=True)
+    branch = np.array(case["branch"], dtype=np.float64, copy=True)
+    gen = np.array(case["gen"], dtype=np.float64, copy=True)
+    ext = bus[:, _BUS_I].astype(np.int64)
+    if len(set(ext.tolist())) != len(ext):
+        raise ValueError("duplicate bus numbers")
+    lut = {int(e): i + 1 for i, e in enumerate(ext)}
+    try:
+        branch[:, _F] = [lut[int(x)] for x in branch[:, _F]]
+        branch[:, _T] = [lut[int(x)] for x in branch[:, _T]]
+        gen[:, _GBUS] = [lut[int(x)] for x in gen[:, _GBUS]]
+    except KeyError as e:
+        raise IndexError(f"branch / generator refers to unknown bus {e}") from None
+    bus[:, _BUS_I] = np.arange(1, len(ext) + 1)
+    out = dict(case)
+    out.update(bus=bus, branch=branch, gen=gen)
+    return out, ext
+
+
+def augment_pack_device(case: dict, n_samples: int, seed: int = 0, device="cuda"):
+    """`augment` + `pack_grids` fused on the device with torch ops: the perturbed,
+    packed batch is produced directly in GPU memory, so building a large synthetic batch costs no
+    host time or PCIe traffic.  Same recipe and packing transform; the random stream differs from
+    the numpy generator of `augment` (the reference's own stream is unseeded anyway)."""
+    dev = torch.device(device)
+    gen_ = torch.Generator(device=dev).manual_seed(int(seed))
+    S = int(n_samples)
+    f64 = dict(dtype=torch.float64, device=dev)
+    bus = torch.as_tensor(np.asarray(case["bus"]), **f64)
+    branch = torch.as_tensor(np.asarray(case["branch"]), **f64)
+    gen = torch.as_tensor(np.asarray(case["gen"]), **f64)
+    N, E, Gn = bus.shape[0], branch.shape[0], gen.shape[0]
+    base = float(case["baseMVA"])
+
+    def U(lo, hi, *shape):
+        return lo + (hi - lo) * torch.rand(*shape, generator=gen_, **f64)
+
+    r = branch[:, _R] * U(0.9, 1.1, S, E)
+    x = branch[:, _X] * U(0.9, 1.1, S, E)
+    b = branch[:, _B] * U(0.9, 1.1, S, E)
+    tap = U(0.8, 1.2, S, E)
+    shift = U(-0.2, 0.2, S, E)
+    vg = gen[:, _VG] * U(0.95, 1.05, S, Gn)
+    span = gen[:, _PMAX] - gen[:, _PMIN]
+    lo, hi = gen[:, _PMIN] + 0.25 * span, 0.75 * span
+    pg = lo + (hi - lo) * torch.rand(S, Gn, generator=gen_, **f64)
+    pd = bus[:, _PD] * U(0.5, 1.5, S, N)
+    pd = pd * (pg.sum(1) / pd.sum(1))[:, None]
+    qd = bus[:, _QD] * U(0.5, 1.5, S, N)
+    f32 = torch.float32
+    buses = torch.empty(S, N, 6, dtype=f32, device=dev)
+    buses[:, :, 0] = bus[:, _BUS_I].to(f32)
+    buses[:, :, 1] = bus[:, _BUS_TYPE].to(f32)
+    buses[:, :, 2] = pd.to(f32) / base
+    buses[:, :, 3] = qd.to(f32) / base
+    buses[:, :, 4] = torch.tensor(1.0, dtype=f32, device=dev) / base
+    buses[:, :, 5] = torch.tensor(-1.0, dtype=f32, device=dev) / base
+    lines = torch.empty(S, E, 7, dtype=f32, device=dev)
+    lines[:, :, 0] = branch[:, _F].to(f32)
+    lines[:, :, 1] = branch[:, _T].to(f32)
+    lines[:, :, 2], lines[:, :, 3], lines[:, :, 4] = r.to(f32), x.to(f32), b.to(f32)
+    tap32 = tap.to(f32)
+    lines[:, :, 5] = torch.where(tap32 == 0, torch.ones_like(tap32), tap32)
+    lines[:, :, 6] = torch.deg2rad(shift.to(f32))
+    gens = torch.empty(S, Gn, 7, dtype=f32, device=dev)
+    gens[:, :, 0] = gen[:, _GBUS].to(f32)
+    gens[:, :, 1] = gen[:, _PMAX].to(f32) / base
+    gens[:, :, 2] = gen[:, _PMIN].to(f32) / base
+    gens[:, :, 3] = pg.to(f32) / base
+    gens[:, :, 4] = vg.to(f32)
+    gens[:, :, 5] = gen[:, _QG].to(f32) / base
+    gens[:, :, 6] = gens[:, :, 3]
+    return buses, lines, gens
+
+
 def make_batch(n_bus: int, n_samples: int, seed: int = 0, topo_seed: int = 0):
     """Synthetic load-perturbed batch of the named case, packed: (buses, lines, generators, label)."""
     case, label = get_case(n_bus, seed=topo_seed)

@@ -163,3 +163,13 @@ def test_large_grid_uses_the_wide_cta_variant(lib):
     _check_against_oracle(model, buses, lines, gens, "700-bus grid")
     info = model._last_plan.launch_info(5, 2, 10, 10, True)
     assert info["threads"] > 384 and info["tmax"] == 1024
+
+
+def test_device_side_augmenter_feeds_the_kernel(lib):
+    """perturb + pack on the GPU, no host round trip; the batch must be a valid input."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    case, _ = pkg.data.get_case(118)
+    b, l, g = pkg.data.augment_pack_device(case, 300, seed=3, device="cuda")
+    assert b.is_cuda and b.shape == (300, 118, 6)
+    _check_against_oracle(model, b.cpu(), l.cpu(), g.cpu(), "device-augmented case118")

@@ -180,3 +180,40 @@ def test_slot_tables_split_high_degree_buses_consistently(lib, n_bus):
         covered += deg[b]
         pos += g
     assert pos == len(sb) and covered == len(t)
+
+
+def test_renumber_buses_makes_noncontiguous_ids_usable():
+    """quirk Q8: real case300-style bus numbers; the reference would raise IndexError at m[dst]."""
+    c = pkg.data.case14()
+    ext_ids = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 9011, 9012, 9533, 14])
+    lut = {i + 1: int(e) for i, e in enumerate(ext_ids)}
+    c2 = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in c.items()}
+    c2["bus"][:, 0] = ext_ids
+    c2["branch"][:, 0] = [lut[int(x)] for x in c["branch"][:, 0]]
+    c2["branch"][:, 1] = [lut[int(x)] for x in c["branch"][:, 1]]
+    c2["gen"][:, 0] = [lut[int(x)] for x in c["gen"][:, 0]]
+    with pytest.raises(IndexError):
+        _host_plan(c2["branch"][:, 0].astype(int) - 1, c2["branch"][:, 1].astype(int) - 1,
+                   c2["gen"][:, 0].astype(int) - 1, 14)
+    back, ext = pkg.data.renumber_buses(c2)
+    assert np.array_equal(ext, ext_ids)
+    for k in ("bus", "branch", "gen"):
+        assert np.array_equal(back[k], c[k])
+    bad = dict(c2); bad["branch"] = c2["branch"].copy(); bad["branch"][0, 0] = 777
+    with pytest.raises(IndexError):
+        pkg.data.renumber_buses(bad)
+
+
+def test_device_augmenter_follows_recipe_on_cpu_device():
+    """augment_pack_device is torch-only: exercised here on the CPU device (the GPU test repeats it)."""
+    case = pkg.data.case14()
+    b, l, g = pkg.data.augment_pack_device(case, 64, seed=5, device="cpu")
+    assert b.shape == (64, 14, 6) and l.shape == (64, 20, 7) and g.shape == (64, 5, 7)
+    assert torch.equal(l[:, :, :2], torch.as_tensor(case["branch"][:, :2], dtype=torch.float32).expand(64, -1, -1))
+    assert ((l[:, :, 5] >= 0.8) & (l[:, :, 5] <= 1.2)).all()
+    assert (l[:, :, 6].abs() <= np.deg2rad(0.2) + 1e-7).all()
+    assert torch.allclose(b[:, :, 2].sum(1), g[:, :, 3].sum(1), rtol=1e-5)          # sum Pd == sum Pg (p.u.)
+    assert torch.equal(g[:, :, 3], g[:, :, 6])
+    assert torch.allclose(b[:, :, 4], torch.full_like(b[:, :, 4], 0.01)) and torch.allclose(b[:, :, 5], torch.full_like(b[:, :, 5], -0.01))
+    b2, _, _ = pkg.data.augment_pack_device(case, 64, seed=5, device="cpu")
+    assert torch.equal(b, b2)
