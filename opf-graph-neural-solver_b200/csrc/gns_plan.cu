@@ -80,33 +80,53 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
 // extra shared memory of the backward kernel, in floats (see gns_backward.cuh)
 int backward_extra_floats(int N, int E, int G, int L, int H, int T);
 
-// Warp w runs on SM sub-partition w % 4.  A warp's bus phase costs ~ (1 + 0.15 * max in-degree of
-// its bus group), so groups are placed longest-first on the sub-partition with the least load
-// that still has a free warp.
-static void balance_warps(const gns_plan* plan, Geometry* g) {
+// Warp w runs on SM sub-partition w % 4.  A warp's bus phase costs ~ (1 + c * max lines walked by
+// a lane of its bus group), c ~ 0.2 forward / 0.3 backward (instruction counts).  Groups are placed
+// longest-first on the sub-partition with the least load that still has a free warp, then pairs of
+// groups are swapped between sub-partitions while that lowers the maximum load (with 10 warps the
+// sub-partitions hold 3,3,2,2 warps, so the heaviest groups must end up on the 2-warp ones).
+static void balance_warps(const gns_plan* plan, Geometry* g, bool backward) {
   const int nw = g->T / 32, spw = 32 / g->NGQ;
-  std::vector<std::pair<float, int>> cost(nw);
+  const float per_line = backward ? 0.3f : 0.2f;
+  std::vector<float> cost(nw, 0.f);
   for (int grp = 0; grp < nw; ++grp) {
     int mx = -1;
     for (int s = grp * spw; s < std::min((grp + 1) * spw, plan->Ns); ++s)
       mx = std::max(mx, plan->slot_in_end[s] - plan->slot_in_begin[s]);
-    cost[grp] = {mx < 0 ? 0.f : 1.f + 0.15f * mx, grp};
+    cost[grp] = mx < 0 ? 0.f : 1.f + per_line * mx;
   }
-  std::stable_sort(cost.begin(), cost.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+  std::vector<int> order(nw);
+  for (int i = 0; i < nw; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
   float load[4] = {0, 0, 0, 0};
-  int used[4] = {0, 0, 0, 0};
-  for (const auto& c : cost) {
+  std::vector<int> bin[4];
+  for (int grp : order) {
     int best = -1;
     for (int sp = 0; sp < 4; ++sp) {
       const int cap = (nw - sp + 3) / 4;           // warps sp, sp+4, ...
-      if (used[sp] >= cap) continue;
+      if ((int)bin[sp].size() >= cap) continue;
       if (best < 0 || load[sp] < load[best]) best = sp;
     }
-    const int warp = best + 4 * used[best];
-    used[best]++;
-    load[best] += c.first;
-    g->grp_of_warp[warp] = (unsigned char)c.second;
+    bin[best].push_back(grp);
+    load[best] += cost[grp];
   }
+  for (bool improved = true; improved;) {            // pairwise swaps that lower the heavier of the two loads
+    improved = false;
+    for (int a = 0; a < 4; ++a)
+      for (int b = a + 1; b < 4; ++b)
+        for (size_t i = 0; i < bin[a].size(); ++i)
+          for (size_t j = 0; j < bin[b].size(); ++j) {
+            const float d = cost[bin[a][i]] - cost[bin[b][j]];
+            const float na = load[a] - d, nb = load[b] + d;
+            if (std::max(na, nb) + 1e-6f < std::max(load[a], load[b])) {
+              std::swap(bin[a][i], bin[b][j]);
+              load[a] = na; load[b] = nb;
+              improved = true;
+            }
+          }
+  }
+  for (int sp = 0; sp < 4; ++sp)
+    for (size_t i = 0; i < bin[sp].size(); ++i) g->grp_of_warp[sp + 4 * i] = (unsigned char)bin[sp][i];
   if (std::getenv("GNS_NO_BALANCE")) for (int w = 0; w < nw; ++w) g->grp_of_warp[w] = (unsigned char)w;
 }
 
@@ -155,7 +175,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
         }
       }
       g.smem_bytes = bytes; g.sm = sm;
-      balance_warps(plan, &g);
+      balance_warps(plan, &g, backward);
       g.nbatch = (int)nb; g.num_sms = plan->num_sms;
       best = g; found = true;
       break;
