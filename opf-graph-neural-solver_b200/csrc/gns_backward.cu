@@ -20,19 +20,82 @@ int backward_ctas(const gns_plan* plan, const ModelDims&, const Geometry& g) {
   return std::min(g.nbatch, plan->num_sms * std::max(1, (int)(plan->smem_optin / std::max<size_t>(g.smem_bytes, 1))));
 }
 
-// packed_grad[p] = sum_w gacc[w][p]
-__global__ void reduce_partials_kernel(const float* __restrict__ gacc, float* __restrict__ packed, long long n,
-                                       int nparts) {
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int w = 0;
-    for (; w + 3 < nparts; w += 4) {
-      s0 += gacc[(size_t)w * n + p];
-      s1 += gacc[(size_t)(w + 1) * n + p];
-      s2 += gacc[(size_t)(w + 2) * n + p];
-      s3 += gacc[(size_t)(w + 3) * n + p];
+// packed index (inside one step's [wstep] block) -> index inside the step's fragment-order accumulator
+// block (FragLayout), or -1 for padding and for the entries the backward kernel never writes (W4 / b4 and
+// the W1 slice behind the fused block, which unfuse_grads_kernel derives).  Mirrors the GEMM calls of
+// gns_backward_kernel one to one.
+std::vector<int32_t> build_frag_map(const ModelDims& md) {
+  const int L = md.L, H = md.H;
+  const bool multi = md.multi != 0;
+  const WLayout W = make_wlayout(L, H, multi);
+  const FragLayout F = make_frag_layout(L, H);
+  std::vector<int32_t> inv(W.wstep, -1);
+  auto put = [&](int packed, int frag) { inv[packed] = frag; };
+  for (int q = 0; q < 3; ++q) {
+    const int fb = q * F.net;
+    if (multi || q == 0) {                       // phi net of this pair (single phi: pair 0 carries it)
+      const int pb = multi ? q * W.phi_size : 0;
+      for (int r = 0; r < H + 1; ++r)
+        for (int c = 0; c < H; ++c) put(pb + (r < H ? W.phi_w2 + r * W.HP : W.phi_b2) + c, fb + F.w2l + frag_index(r, c));
+      for (int r = 0; r < 5; ++r)
+        for (int c = 0; c < H; ++c) put(pb + W.phi_w1f + r * W.HP + c, fb + F.w1f + frag_index(r, c));
+      for (int r = 0; r < L + 1; ++r)
+        for (int c = 0; c < H; ++c) put(pb + (r < L ? W.phi_w1m + r * W.HP : W.phi_b1) + c, fb + F.w1m + frag_index(r, c));
     }
-    for (; w < nparts; ++w) s0 += gacc[(size_t)w * n + p];
+    const int lb = W.off_ln[0] + q * W.ln_size_s;
+    if (q < 2) {
+      for (int r = 0; r < H + 1; ++r) put(lb + (r < H ? W.ln_wo + r : W.ln_bo_s), fb + F.out + r);
+    } else {
+      for (int r = 0; r < L; ++r)
+        for (int c = 0; c < H + 1; ++c) put(lb + (c < H ? W.ln_wo + r * W.HP + c : W.ln_bo_m + r), fb + F.out + frag_index(r, c));
+    }
+    for (int r = 0; r < H + 1; ++r)
+      for (int c = 0; c < H; ++c) put(lb + (r < H ? W.ln_w2 + r * W.HP : W.ln_b2) + c, fb + F.w2 + frag_index(r, c));
+    const int mfb = W.off_mf[0] + q * W.mf_size;
+    for (int r = 0; r < 4 + L + H + 2; ++r)
+      for (int c = 0; c < H; ++c) {
+        const int packed = r < 4 + L ? lb + W.ln_w1 + r * W.HP + c
+                                     : (r < 4 + L + H + 1 ? mfb + (r - 4 - L) * W.HP + c : lb + W.ln_b1 + c);
+        put(packed, fb + F.w1 + frag_index(r, c));
+      }
+  }
+  return inv;
+}
+
+static const int32_t* get_frag_map(gns_plan* plan, const ModelDims& md) {
+  auto key = std::make_tuple(md.L, md.H, md.multi);
+  auto it = plan->frag_maps.find(key);
+  if (it != plan->frag_maps.end()) return it->second;
+  const std::vector<int32_t> inv = build_frag_map(md);
+  int32_t* d = nullptr;
+  if (cudaMalloc(&d, inv.size() * sizeof(int32_t)) != cudaSuccess ||
+      cudaMemcpy(d, inv.data(), inv.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("frag map upload failed");
+    return nullptr;
+  }
+  plan->frag_maps.emplace(key, d);
+  return d;
+}
+
+// packed_grad[k][p] = sum_w gacc[w][k][inv[p]]   (0 where inv[p] < 0)
+__global__ void reduce_partials_kernel(const float* __restrict__ gacc, const int32_t* __restrict__ inv,
+                                       float* __restrict__ packed, int K, int wstep, int fstep, int nparts) {
+  const long long n = (long long)K * wstep, part = (long long)K * fstep;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(p / wstep);
+    const int f = inv[p - (long long)k * wstep];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (f >= 0) {
+      const float* src = gacc + (size_t)k * fstep + f;
+      int w = 0;
+      for (; w + 3 < nparts; w += 4) {
+        s0 += src[(size_t)w * part];
+        s1 += src[(size_t)(w + 1) * part];
+        s2 += src[(size_t)(w + 2) * part];
+        s3 += src[(size_t)(w + 3) * part];
+      }
+      for (; w < nparts; ++w) s0 += src[(size_t)w * part];
+    }
     packed[p] = (s0 + s1) + (s2 + s3);
   }
 }
@@ -102,7 +165,10 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
   char* wsb = static_cast<char*>(workspace);
   const int nwarps = gb.T / 32;
-  const size_t per_part = (size_t)md.K * W.wstep;
+  const FragLayout FL = make_frag_layout(md.L, md.H);
+  const size_t per_part = (size_t)md.K * FL.step;
+  const int32_t* d_inv = get_frag_map(plan, md);
+  if (!d_inv) return -2;
   const int nparts = gb.ctas * nwarps;
   float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
   float* packed_grad = reinterpret_cast<float*>(wsb + ws.packed_grad);
@@ -120,12 +186,14 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.buses = buses; a.lines = lines; a.gens = gens;
   a.ckpt = reinterpret_cast<const float*>(wsb + ws.ckpt);
   a.pglob = reinterpret_cast<const float*>(wsb + ws.pglob);
+  a.act = reinterpret_cast<const float*>(wsb + ws.act);
   a.grad_total = grad_total; a.grad_last = grad_last; a.grad_v = grad_v; a.grad_theta = grad_theta;
   a.gacc = gacc;
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
   a.NGs = row_stride(plan->Ns * gb.G); a.EGs = row_stride(plan->E * gb.G);
-  a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G);
+  a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G); a.EGs_f = row_stride(plan->E * gf.G);
+  a.al = make_act_layout(md.H, md.multi ? 3 : 1, a.NGs_f, a.EGs_f);
   std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);
   a.sm = gb.sm;
   a.bs = make_bwd_smem(plan->Ns, plan->E, gb.G, md.L, md.H, md.L, nwarps, md.L > 32);
@@ -136,8 +204,8 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   if (e != cudaSuccess) { set_error(std::string("backward launch: ") + cudaGetErrorString(e)); return -2; }
   {
     const int th = 256;
-    const int bl = (int)std::min<long long>(((long long)per_part + th - 1) / th, 2048);
-    reduce_partials_kernel<<<bl, th, 0, st>>>(gacc, packed_grad, (long long)per_part, nparts);
+    const int bl = (int)std::min<long long>(((long long)md.K * W.wstep + th - 1) / th, 2048);
+    reduce_partials_kernel<<<bl, th, 0, st>>>(gacc, d_inv, packed_grad, md.K, W.wstep, FL.step, nparts);
     const int nphi = md.multi ? 3 : 1, PO = md.multi ? md.L : 1;
     const int tot = md.K * (nphi * PO * md.H + nphi * PO + 3 * PO * md.H);
     unfuse_grads_kernel<<<(tot + th - 1) / th, th, 0, st>>>(packed_grad, a.params, W, md.K);

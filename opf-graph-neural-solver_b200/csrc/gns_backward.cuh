@@ -4,9 +4,9 @@
 // Per step k = K-1 .. 0 (state_k = checkpoint written by the forward kernel):
 //   1. physics adjoint: loss -> dP' -> (lambda / p_global coupling, line flows) -> v', theta'.
 //      All scatter-adds of the forward become CSR gathers here, so there are no atomics.
-//   2. MLP adjoint per bus, thread-local: the bus thread recomputes its phi / L-net
-//      activations from state_k and back-propagates them (dX), exactly mirroring the
-//      bus-centric forward.
+//   2. MLP adjoint per bus, thread-local: the bus thread reads the hidden activations the
+//      forward kernel kept (ActLayout: post-LeakyReLU values, whose sign gives the slope) and
+//      back-propagates them (dX), mirroring the bus-centric forward.  Nothing is recomputed.
 //   3. weight gradients (the only GEMM-shaped work): dW^T[w][o] = sum_items wide[w] * hid[o].
 //      Each warp transposes the per-item vectors of its 32 items through a private shared
 //      memory tile ([feature][item]); lane r then owns row r of dW^T and runs over the 32
@@ -28,7 +28,10 @@ namespace gns {
 #ifndef GNS_TG_PREFETCH
 #define GNS_TG_PREFETCH 1
 #endif
-constexpr int kTS = 36;   // tile row stride in floats: 32 items + 4 (odd number of 16 B groups)
+#ifndef GNS_KTS
+#define GNS_KTS 48
+#endif
+constexpr int kTS = GNS_KTS;   // tile row stride in floats: 48 = 16 mod 32, so the 128-bit fragment loads of 8 rows x 4 quads are conflict-free
 
 struct BwdSmem {          // offsets in floats from SmemPlan.extra
   int adj;                // [(4+L)][NGs]  adjoint of (v, theta, dP, dQ, m)
@@ -62,14 +65,16 @@ struct BwdArgs {
   const float* buses; const float* lines; const float* gens;
   const float* ckpt;        // forward checkpoints [nbatch_f][K][(4+L)*NGs_f], grid-interleaved with G_f
   const float* pglob;       // [nbatch_f][K][G_f]
+  const float* act;         // [nbatch_f][K][ActLayout.total] hidden activations kept by the forward kernel
   const float* grad_total; const float* grad_last; const float* grad_v; const float* grad_theta;
-  float* gacc;              // [ctas*nwarps][K*wstep] per-warp gradient accumulators (zeroed by the host)
+  float* gacc;              // [ctas*nwarps][K][FragLayout.step] per-warp gradient accumulators (zeroed by the host)
   float* mscratch;          // [ctas][2][L][NGs] m and adj m rows when they do not fit shared memory (L > 32)
   const uint16_t* topo;
   long long S;
   int N, Ns, E, Gn, K, NGQ, G, nbatch;
   int NGs, EGs;
-  int Gf, NGs_f;            // forward geometry of the checkpoints
+  int Gf, NGs_f, EGs_f;     // forward geometry of the checkpoints
+  ActLayout al;
   unsigned char grp_of_warp[32];
   SmemPlan sm;
   BwdSmem bs;
@@ -138,18 +143,102 @@ __device__ __forceinline__ void tile_gemm_chunk(int rb, int re, RowFn rowfn, con
   }
 }
 
-template <int C, int R, class RowFn, class OutFn>
-__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hid, float* __restrict__ g, OutFn outfn) {
-  constexpr int FULL = (R / 32) * 32, REM = R - FULL;
-  if (FULL > 0) tile_gemm_chunk<C, 1>(0, FULL, rowfn, hid, g, outfn);
-  if (REM > 0) {
-    if (GNS_TG_SPLIT && REM > 16 && REM <= 24) {          // 17..24 rows: 16 rows two-way + the rest four-way
-      tile_gemm_chunk<C, 2>(FULL, FULL + 16, rowfn, hid, g, outfn);
-      tile_gemm_chunk<C, 4>(FULL + 16, R, rowfn, hid, g, outfn);
-    } else {
-      constexpr int P = GNS_TG_SPLIT ? (REM <= 8 ? 4 : (REM <= 16 ? 2 : 1)) : 1;
-      tile_gemm_chunk<C, P>(FULL, R, rowfn, hid, g, outfn);
+// ---- weight-gradient tiles on the tensor cores: mma.sync m16n8k8 TF32 with a 3-term split ----
+// D[hid c][wide r] += sum_item hid_c[item] * row_r[item]: M = hidden columns (C <= 16), N = 8 wide rows per
+// tile, K = the warp's 32 items.  Every FP32 operand x is split into big = x with the low 13 mantissa
+// bits cleared (exactly a TF32 number) and small = x - big (exact in FP32; the tensor core keeps its
+// top 10 mantissa bits), and D += big*big + big*small + small*big: the dropped terms are below 2^-20
+// relative per product, against 2^-11 for plain TF32, so the FP32 parity tolerances hold.
+// The k index of an MMA is a free permutation as long as A and B agree: k slot t (t+4) of MMA i is item
+// 4t+i (16+4t+i), so both fragments come straight from two LDS.128 per row and need no shuffles.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
+  big = __float_as_uint(x) & 0xffffe000u;
+  small = __float_as_uint(x - __uint_as_float(big));
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, const float (&d)[4]) {   // fire-and-forget: no load, no scoreboard wait
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d[0]), "f"(d[1]), "f"(d[2]), "f"(d[3]) : "memory");
+}
+
+// gfrag: this call's block of the warp-private accumulator (FragLayout); only this warp ever adds to it,
+// in program order, so the reductions are deterministic.
+template <int C, int R, class RowFn>
+__device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hid, float* __restrict__ gfrag) {
+  static_assert(C <= 16, "hidden side must fit one m16 tile");
+  const int lane = threadIdx.x & 31, gi = lane >> 2, t = lane & 3;
+  // A fragments (hidden columns gi and gi+8) for the four MMAs of the 32 items
+  uint32_t ab[4][4], as[4][4];            // [mma i][a0..a3], big and small parts
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* h0 = hid + gi * kTS + 4 * t;
+    const float* h1 = hid + (gi + 8) * kTS + 4 * t;
+    const float4 lo0 = (gi < C) ? *reinterpret_cast<const float4*>(h0) : z4;
+    const float4 hi0 = (gi < C) ? *reinterpret_cast<const float4*>(h0 + 16) : z4;
+    const float4 lo1 = (C > 8 && gi + 8 < C) ? *reinterpret_cast<const float4*>(h1) : z4;
+    const float4 hi1 = (C > 8 && gi + 8 < C) ? *reinterpret_cast<const float4*>(h1 + 16) : z4;
+    const float l0[4] = {lo0.x, lo0.y, lo0.z, lo0.w}, u0[4] = {hi0.x, hi0.y, hi0.z, hi0.w};
+    const float l1[4] = {lo1.x, lo1.y, lo1.z, lo1.w}, u1[4] = {hi1.x, hi1.y, hi1.z, hi1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      split_tf32(l0[i], ab[i][0], as[i][0]);
+      split_tf32(l1[i], ab[i][1], as[i][1]);
+      split_tf32(u0[i], ab[i][2], as[i][2]);
+      split_tf32(u1[i], ab[i][3], as[i][3]);
     }
+  }
+  constexpr int NT = (R + 7) / 8;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int row = nt * 8 + gi;
+    const bool rv = (nt * 8 + 8 <= R) || (row < R);
+    const float* rp = rowfn(rv ? row : 0) + 4 * t;
+    float4 blo = *reinterpret_cast<const float4*>(rp);
+    float4 bhi = *reinterpret_cast<const float4*>(rp + 16);
+    if (!rv) { blo = make_float4(0.f, 0.f, 0.f, 0.f); bhi = blo; }
+    const float bl[4] = {blo.x, blo.y, blo.z, blo.w}, bu[4] = {bhi.x, bhi.y, bhi.z, bhi.w};
+    uint32_t bb0[4], bs0[4], bb1[4], bs1[4];
+    float di[2][4];                       // two accumulator chains: consecutive MMAs are independent
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      split_tf32(bl[i], bb0[i], bs0[i]);
+      split_tf32(bu[i], bb1[i], bs1[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { di[0][j] = 0.f; di[1][j] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mma_tf32(di[i & 1], as[i], bb0[i], bb1[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mma_tf32(di[i & 1], ab[i], bs0[i], bs1[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mma_tf32(di[i & 1], ab[i], bb0[i], bb1[i]);
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = di[0][j] + di[1][j];
+    red_add_v4(gfrag + nt * 128 + lane * 4, d);
+  }
+}
+
+#ifndef GNS_TG_MMA
+#define GNS_TG_MMA 1
+#endif
+
+// one weight-gradient GEMM call: rows r < R (wide side) x C hidden columns over the warp's 32 items, added
+// into the call's accumulator block.  C == 1 (output layer of the scalar nets) keeps the lane-per-row
+// FFMA form and stores cell r at gfrag[r].
+template <int C, int R, class RowFn>
+__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hid, float* __restrict__ gfrag) {
+  if constexpr (C > 1) {
+    tile_gemm_mma<C, R>(rowfn, hid, gfrag);
+  } else {
+    static_assert(R <= 16, "scalar path");
+    constexpr int P = GNS_TG_SPLIT ? (R <= 8 ? 4 : 2) : 1;
+    tile_gemm_chunk<C, P>(0, R, rowfn, hid, gfrag, [](int r, int) { return r; });
   }
 }
 
@@ -161,8 +250,8 @@ template <int L, int H, bool MULTI, int TMAX>
 __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) {
   constexpr bool MG = L > 32;
   constexpr WLayout W = make_wlayout(L, H, MULTI);
+  constexpr FragLayout FL = make_frag_layout(L, H);
   constexpr int HP = pad4(H);
-  constexpr int PO = MULTI ? L : 1;
   // tile row map
   constexpr int R_ONES = 0;
   constexpr int R_HID = 1;                 // H+1 rows
@@ -198,7 +287,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const int gq = lane % NGQ;
   const bool slot_on = slot < a.Ns;           // owns a bus slot (primary or twin)
   float* const tile = smem + a.sm.extra + a.bs.tiles + warp * a.bs.trows * kTS;
-  float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * W.wstep);
+  float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * FL.step);
 
   // zero all dynamic shared memory once: padding lanes and tail rows must hold finite values
   for (int i = tid; i < a.sm.total_floats; i += T) smem[i] = 0.f;
@@ -296,8 +385,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #if GNS_BWD_L2PREFETCH
       {   // pull this warp's step-k accumulator block towards L2 now; the read-modify-writes of the
           // weight-gradient tiles then see L2 latency instead of DRAM latency
-        const char* blk = reinterpret_cast<const char*>(gacc_w + (size_t)k * W.wstep);
-        for (int i = lane * 128; i < W.wstep * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
+        const char* blk = reinterpret_cast<const char*>(gacc_w + (size_t)k * FL.step);
+        for (int i = lane * 128; i < FL.step * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
       }
 #endif
       {
@@ -440,75 +529,23 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int i = tid * 128; i < (int)(ck_stride * 4); i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
         }
       }
-      float* const gk = gacc_w + (size_t)k * W.wstep;
+      float* const gk = gacc_w + (size_t)k * FL.step;
       {
-        const float* st = s_state + nb;
-        const float* sm_m = m_rows + nb;
         float* adjrow = s_adj + nb;
         float* adjm = am_rows + nb;
-        float st4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) st4[i] = st[i * NG];
         float adj4[4] = {0.f, 0.f, 0.f, 0.f};
         const float* rows_state = s_state + 32 * grp;          // [f][item] rows of this warp's 32 items
         const float* rows_m = m_rows + 32 * grp;
         const float* rows_am = am_rows + 32 * grp;
-        float A[H], P[H], adjA[H];
+        // this grid's column of the activations the forward kernel kept for step k (no recompute here)
+        const float* const act_k = a.act + ((size_t)bf * K + k) * (size_t)a.al.total + cf;
+        const size_t NGf = (size_t)a.NGs_f, EGf = (size_t)a.EGs_f;
+        float adjA[H];
 #pragma unroll
-        for (int o = 0; o < H; ++o) { A[o] = 0.f; P[o] = 0.f; adjA[o] = 0.f; }
-
-        // forward recompute of one phi net for this bus: P and the aggregate A
-        auto phi_forward = [&](const float* wphi) {
-          {
-            float b[HP];
-            load_row<HP>(b, wphi + W.phi_b1);
-#pragma unroll
-            for (int o = 0; o < H; ++o) P[o] = b[o];
-          }
-#pragma unroll 4
-          for (int i = 0; i < L; ++i) {
-            float x[1] = {sm_m[i * NG]};
-            float (&Pv)[H][1] = reinterpret_cast<float (&)[H][1]>(P);
-            row_axpy<H, HP, 1>(Pv, x, wphi + W.phi_w1m + i * HP);
-          }
-#pragma unroll
-          for (int o = 0; o < H; ++o) A[o] = 0.f;
-          for (int e = e_in0; e < e_in1; ++e) {
-            const float* lf = s_linef + (int)t_ini[e] * G + gq;
-            const float* wp = wphi + opaque_zero();
-            float z[H][1], z2[H][1];
-#pragma unroll
-            for (int o = 0; o < H; ++o) z[o][0] = P[o];
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              float x[1] = {lf[c * EG]};
-              row_axpy<H, HP, 1>(z, x, wp + W.phi_w1f + c * HP);
-            }
-            {
-              float b[HP];
-              load_row<HP>(b, wp + W.phi_b2);
-#pragma unroll
-              for (int o = 0; o < H; ++o) { z2[o][0] = b[o]; z[o][0] = lrelu(z[o][0]); }
-            }
-#pragma unroll
-            for (int j = 0; j < H; ++j) row_axpy<H, HP, 1>(z2, z[j], wp + W.phi_w2 + j * HP);
-#pragma unroll
-            for (int o = 0; o < H; ++o) A[o] += lrelu(z2[o][0]);
-          }
-          if (warp_has_twins) {   // combine the partial aggregates of a bus split over twin lanes
-#pragma unroll
-            for (int d = 1; d < 4; d *= 2) {
-#pragma unroll
-              for (int o = 0; o < H; ++o) {
-                const float t = __shfl_xor_sync(0xffffffffu, A[o], d * NGQ);
-                if (gsz > d) A[o] += t;
-              }
-            }
-          }
-        };
+        for (int o = 0; o < H; ++o) adjA[o] = 0.f;
 
         // adjoint of one phi net given adjA: line loop, dW2 / db2 / dW1f, adjP, dW1m / db1, adj m
-        auto phi_backward = [&](const float* wphi, float* gphi) {
+        auto phi_backward = [&](const float* wphi, float* gphi, const float* actl) {
           float adjP[H];
 #pragma unroll
           for (int o = 0; o < H; ++o) adjP[o] = 0.f;
@@ -519,54 +556,38 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int it = 0; it < warp_max_deg; ++it) {
             const bool live = slot_on && (it < deg);
             const float* wp = wphi + opaque_zero();
-            float z[H][1], z2[H][1], d2[H], d1[H], feat[5];
-            const float* lf = s_linef + (int)t_ini[live ? e_in0 + it : 0] * G + gq;
+            const int e = live ? e_in0 + it : 0;                 // position in the in-list
+            const float* ap = actl + (size_t)e * a.Gf;
+            float h1[H], h2[H], d2[H][1], d1[H], feat[5];
 #pragma unroll
-            for (int o = 0; o < H; ++o) z[o][0] = P[o];
+            for (int o = 0; o < H; ++o) { h1[o] = __ldg(ap + o * EGf); h2[o] = __ldg(ap + (H + o) * EGf); }
+            const float* lf = s_linef + (int)t_ini[e] * G + gq;
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              feat[c] = lf[c * EG];
-              float x[1] = {feat[c]};
-              row_axpy<H, HP, 1>(z, x, wp + W.phi_w1f + c * HP);
-            }
-            float h1[H][1];
-            {
-              float b[HP];
-              load_row<HP>(b, wp + W.phi_b2);
+            for (int c = 0; c < 5; ++c) feat[c] = lf[c * EG];
 #pragma unroll
-              for (int o = 0; o < H; ++o) { z2[o][0] = b[o]; h1[o][0] = lrelu(z[o][0]); }
-            }
+            for (int o = 0; o < H; ++o) d2[o][0] = live ? adjA[o] * lrelu_grad(h2[o]) : 0.f;
 #pragma unroll
-            for (int j = 0; j < H; ++j) row_axpy<H, HP, 1>(z2, h1[j], wp + W.phi_w2 + j * HP);
-#pragma unroll
-            for (int o = 0; o < H; ++o) d2[o] = live ? adjA[o] * lrelu_grad(z2[o][0]) : 0.f;
-            {
-              float (&d2v)[H][1] = reinterpret_cast<float (&)[H][1]>(d2);
-#pragma unroll
-              for (int j = 0; j < H; ++j) {
-                float t[1] = {0.f};
-                row_dot<H, HP, 1>(t, d2v, wp + W.phi_w2 + j * HP);
-                d1[j] = t[0] * lrelu_grad(z[j][0]);
-                adjP[j] += d1[j];
-              }
+            for (int j = 0; j < H; ++j) {
+              float t[1] = {0.f};
+              row_dot<H, HP, 1>(t, d2, wp + W.phi_w2 + j * HP);
+              d1[j] = t[0] * lrelu_grad(h1[j]);
+              adjP[j] += d1[j];
             }
             __syncwarp();
 #pragma unroll
             for (int o = 0; o < H; ++o) {
-              tile[(R_HID + o) * kTS + lane] = d2[o];
+              tile[(R_HID + o) * kTS + lane] = d2[o][0];
               tile[(R_HID2 + o) * kTS + lane] = d1[o];
-              tile[(R_WIDE + o) * kTS + lane] = live ? h1[o][0] : 0.f;
+              tile[(R_WIDE + o) * kTS + lane] = live ? h1[o] : 0.f;
             }
 #pragma unroll
             for (int c = 0; c < 5; ++c) tile[(R_WIDE + H + 1 + c) * kTS + lane] = live ? feat[c] : 0.f;
             __syncwarp();
             // dW2^T[j][o] += h1[j] d2[o];  db2[o] += d2[o]
             tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
-                         tile + R_HID * kTS, gphi,
-                         [&](int r, int c) { return (r < H ? W.phi_w2 + r * HP : W.phi_b2) + c; });
+                         tile + R_HID * kTS, gphi + FL.w2l);
             // dW1f^T[c5][o] += feat[c5] d1[o]
-            tile_gemm_r<H, 5>([&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi,
-                         [&](int r, int c) { return W.phi_w1f + r * HP + c; });
+            tile_gemm_r<H, 5>([&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi + FL.w1f);
           }
           if (warp_has_twins) {   // the bus owner needs the sum over its twins
 #pragma unroll
@@ -584,8 +605,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           __syncwarp();
           // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
           tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * NG : tile + R_ONES * kTS; },
-                       tile + R_HID * kTS, gphi,
-                       [&](int r, int c) { return (r < L ? W.phi_w1m + r * HP : W.phi_b1) + c; });
+                       tile + R_HID * kTS, gphi + FL.w1m);
           {
             float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
 #pragma unroll 4
@@ -602,46 +622,22 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           const int q = (qq == 0) ? 2 : qq - 1;      // m-net first: it reads adj m' before anyone adds to it
           const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;
-          float* gphi = gk + (MULTI ? q * W.phi_size : 0);
-          float* gln = gk + W.off_ln[0] + q * W.ln_size_s;
-          if (MULTI || qq == 0) phi_forward(wphi);
-
-          // ---- L-net forward recompute; S_i staged as wide rows of dW1 ----
-          float zL[H][1], z2L[H][1];
-          {
-            float b[HP];
-            load_row<HP>(b, wln + W.ln_b1);
-#pragma unroll
-            for (int o = 0; o < H; ++o) zL[o][0] = b[o];
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { float x[1] = {st4[i]}; row_axpy<H, HP, 1>(zL, x, wln + W.ln_w1 + i * HP); }
-#pragma unroll 4
-          for (int i = 0; i < L; ++i) { float x[1] = {sm_m[i * NG]}; row_axpy<H, HP, 1>(zL, x, wln + W.ln_w1 + (4 + i) * HP); }
-          __syncwarp();
+          float* gphi = gk + (MULTI ? q * FL.net : 0);   // accumulator blocks of this pair (fragment order)
+          float* gln = gk + q * FL.net;
           const float* wmf = s_w + W.off_mf[0] + q * W.mf_size;     // fused block M (H rows) and c (1 row)
+
+          // ---- activations of this bus and pair kept by the forward kernel: A, h1, h2 of the L-net ----
+          float h1L[H], h2L[H];
           {
+            const float* ab = act_k + (size_t)(q * 3 * H) * NGf + (size_t)n * a.Gf;
+            float Aq[H];
 #pragma unroll
-            for (int j = 0; j < H; ++j) {
-              float aj[1] = {A[j]};
-              row_axpy<H, HP, 1>(zL, aj, wmf + j * HP);
-              stage(R_S + j, A[j]);                                  // wide rows of dM
-            }
-            float dg[1] = {degf};
-            row_axpy<H, HP, 1>(zL, dg, wmf + H * HP);
+            for (int o = 0; o < H; ++o) { Aq[o] = __ldg(ab + o * NGf); h1L[o] = __ldg(ab + (H + o) * NGf); h2L[o] = __ldg(ab + (2 * H + o) * NGf); }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < H; ++j) stage(R_S + j, Aq[j]);       // wide rows of dM
             stage(R_S + H, degf);                                    // wide row of dc
           }
-          float h1L[H][1], h2L[H][1];
-          {
-            float b[HP];
-            load_row<HP>(b, wln + W.ln_b2);
-#pragma unroll
-            for (int o = 0; o < H; ++o) { z2L[o][0] = b[o]; h1L[o][0] = lrelu(zL[o][0]); }
-          }
-#pragma unroll
-          for (int j = 0; j < H; ++j) row_axpy<H, HP, 1>(z2L, h1L[j], wln + W.ln_w2 + j * HP);
-#pragma unroll
-          for (int o = 0; o < H; ++o) h2L[o][0] = lrelu(z2L[o][0]);
 
           // ---- output layer adjoint and its weight gradient ----
           float dh2[H][1];
@@ -652,13 +648,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             float gv[1] = {g};
             row_axpy<H, HP, 1>(dh2, gv, wln + W.ln_wo);
 #pragma unroll
-            for (int o = 0; o < H; ++o) stage(R_WIDE + o, h2L[o][0]);
+            for (int o = 0; o < H; ++o) stage(R_WIDE + o, h2L[o]);
             stage(R_HID, g);
             __syncwarp();
             // dWout[j] += g h2[j];  dbout += g      (rows = [h2 (H), ones], one column g)
             tile_gemm_r<1, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
-                         tile + R_HID * kTS, gln,
-                         [&](int r, int) { return r < H ? W.ln_wo + r : W.ln_bo_s; });
+                         tile + R_HID * kTS, gln + FL.out);
           } else {
 #pragma unroll 2
             for (int i = 0; i < L; ++i) {
@@ -666,51 +661,43 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
               row_axpy<H, HP, 1>(dh2, gm, wln + W.ln_wo + i * HP);
             }
 #pragma unroll
-            for (int o = 0; o < H; ++o) stage(R_HID + o, h2L[o][0]);
+            for (int o = 0; o < H; ++o) stage(R_HID + o, h2L[o]);
             stage(R_HID + H, 1.f);
             __syncwarp();
             // dWout[i][j] += adjm'[i] h2[j];  dbout[i] += adjm'[i]    (rows = adj m' rows in place)
-            tile_gemm_r<H + 1, L>([&](int r) { return rows_am + r * NG; }, tile + R_HID * kTS, gln,
-                             [&](int r, int c) { return c < H ? W.ln_wo + r * HP + c : W.ln_bo_m + r; });
+            tile_gemm_r<H + 1, L>([&](int r) { return rows_am + r * NG; }, tile + R_HID * kTS, gln + FL.out);
           }
           __syncwarp();
           // ---- second layer ----
           float d2[H][1], d1[H][1];
 #pragma unroll
           for (int o = 0; o < H; ++o) {
-            d2[o][0] = dh2[o][0] * lrelu_grad(z2L[o][0]);
+            d2[o][0] = dh2[o][0] * lrelu_grad(h2L[o]);
             stage(R_HID + o, d2[o][0]);
-            stage(R_WIDE + o, h1L[o][0]);
+            stage(R_WIDE + o, h1L[o]);
           }
           __syncwarp();
           tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
-                       tile + R_HID * kTS, gln,
-                       [&](int r, int c) { return (r < H ? W.ln_w2 + r * HP : W.ln_b2) + c; });
+                       tile + R_HID * kTS, gln + FL.w2);
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             float t[1] = {0.f};
             row_dot<H, HP, 1>(t, d2, wln + W.ln_w2 + j * HP);
-            d1[j][0] = t[0] * lrelu_grad(zL[j][0]);
+            d1[j][0] = t[0] * lrelu_grad(h1L[j]);
           }
           __syncwarp();
           // ---- first layer: dW1^T[i][o] += x[i] d1[o] with x = [v,theta,dP,dQ, m, S], db1 += d1 ----
 #pragma unroll
           for (int o = 0; o < H; ++o) stage(R_HID + o, d1[o][0]);
           __syncwarp();
-          {
-            const int mf_rel = (W.off_mf[0] + q * W.mf_size) - (W.off_ln[0] + q * W.ln_size_s);   // dM / dc block, relative to gln
-            // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
-            tile_gemm_r<H, 4 + L + H + 2>(
-                [&](int r) {
-                  return r < 4 ? rows_state + r * NG
-                         : r < 4 + L ? rows_m + (r - 4) * NG
-                                   : (r < 4 + L + H + 1 ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
-                },
-                tile + R_HID * kTS, gln,
-                [&](int r, int c) {
-                  return (r < 4 + L ? W.ln_w1 + r * HP : (r < 4 + L + H + 1 ? mf_rel + (r - 4 - L) * HP : W.ln_b1)) + c;
-                });
-          }
+          // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
+          tile_gemm_r<H, 4 + L + H + 2>(
+              [&](int r) {
+                return r < 4 ? rows_state + r * NG
+                       : r < 4 + L ? rows_m + (r - 4) * NG
+                                 : (r < 4 + L + H + 1 ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
+              },
+              tile + R_HID * kTS, gln + FL.w1);
           __syncwarp();
           // ---- dX of the first layer ----
 #pragma unroll
@@ -736,7 +723,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             adjA[j] += t[0];
           }
           __syncwarp();
-          if (MULTI || qq == 2) phi_backward(wphi, gphi);
+          if (MULTI || qq == 2)
+            phi_backward(wphi, gphi, act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * EGf);
         }
         if (bus_on) {
           adjrow[0 * NG] = adjv + adj4[0];

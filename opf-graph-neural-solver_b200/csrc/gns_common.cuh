@@ -86,6 +86,53 @@ __host__ __device__ constexpr WLayout make_wlayout(int L, int H, bool multi) {
 }
 
 // ---------------------------------------------------------------------------------
+// Gradient accumulators of the backward kernel, in MMA-fragment order.  Every weight-gradient GEMM
+// call owns a block of NT x 128 floats ([8-row tile][lane][4 accumulator cells]) inside its warp's
+// private accumulator, so a lane adds its four cells with one 128-bit reduction and no index
+// arithmetic; build_frag_map() (host) inverts the order once per model shape.
+// Per pair q: phi per-line W2/b2 (11 wide rows), phi per-line W1f (5), phi W1m/b1 (L+1),
+// L-net output layer (m-net: L rows x (H+1) columns; scalar nets: H+1 values, stored directly),
+// L-net second layer (H+1), L-net first layer + fused block + bias (4+L+H+2).
+// ---------------------------------------------------------------------------------
+struct FragLayout { int w2l, w1f, w1m, out, w2, w1, net, step; };
+__host__ __device__ constexpr int frag_tiles(int rows) { return (rows + 7) / 8; }
+__host__ __device__ constexpr FragLayout make_frag_layout(int L, int H) {
+  FragLayout f{};
+  int o = 0;
+  f.w2l = o; o += 128 * frag_tiles(H + 1);
+  f.w1f = o; o += 128 * frag_tiles(5);
+  f.w1m = o; o += 128 * frag_tiles(L + 1);
+  f.out = o; o += 128 * frag_tiles(L);
+  f.w2 = o; o += 128 * frag_tiles(H + 1);
+  f.w1 = o; o += 128 * frag_tiles(4 + L + H + 2);
+  f.net = o;
+  f.step = 3 * o;
+  return f;
+}
+// position of cell (wide row r, hidden column c) inside a call's block
+__host__ __device__ constexpr int frag_index(int r, int c) {
+  return (r / 8) * 128 + ((c % 8) * 4 + (r % 8) / 2) * 4 + (r % 2) + 2 * (c / 8);
+}
+
+// ---------------------------------------------------------------------------------
+// Activation checkpoints (training only).  Besides the state entering every step, the forward
+// kernel keeps the post-LeakyReLU hidden activations of every MLP evaluation, so that the backward
+// kernel neither recomputes the forward nor needs the pre-activations (h > 0 <=> z > 0):
+//   per bus and pair q:   A (aggregate, H), h1 and h2 of the L-net (H each)    rows [q][3H][NGs]
+//   per line and phi net: h1 and h2 of the phi net (H each)                    rows [p][2H][EGs]
+// in the forward kernel's grid-interleaved layout; a line is addressed by its position in the
+// plan's in-list (each position is walked by exactly one slot).  172 floats per bus and step on
+// case300: 867 KB per grid for K=4, streamed once out and once in (~1.3 TB/s at 0.75 M grids/s).
+// ---------------------------------------------------------------------------------
+struct ActLayout { int line_off; int total; };
+__host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int NGs, int EGs) {
+  ActLayout a{};
+  a.line_off = 3 * 3 * H * NGs;
+  a.total = a.line_off + nphi * 2 * H * EGs;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------
 // Topology index block (shared by all grids; copied to shared memory once per CTA).
 // All entries are uint16 (n_bus, n_line < 65536).
 // ---------------------------------------------------------------------------------
@@ -158,8 +205,18 @@ template <> struct VecIO<4> {
   }
 };
 
+// streaming global stores / loads of VG consecutive grids (activation checkpoints)
+template <int VG> __device__ __forceinline__ void stg_stream(float* p, const float (&x)[VG]);
+template <> __device__ __forceinline__ void stg_stream<1>(float* p, const float (&x)[1]) { __stcs(p, x[0]); }
+template <> __device__ __forceinline__ void stg_stream<2>(float* p, const float (&x)[2]) {
+  __stcs(reinterpret_cast<float2*>(p), make_float2(x[0], x[1]));
+}
+template <> __device__ __forceinline__ void stg_stream<4>(float* p, const float (&x)[4]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
+}
+
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }
-__device__ __forceinline__ float lrelu_grad(float z) { return z > 0.f ? 1.f : kSlope; }
+__device__ __forceinline__ float lrelu_grad(float z) { return z > 0.f ? 1.f : kSlope; }   // also valid on h = lrelu(z)
 
 // sin and cos of one float, branch-free: three-constant Cody-Waite reduction by pi/2 with FMAs,
 // then minimax polynomials on [-pi/4, pi/4].  Max abs error 9.3e-8 for |x| <= 1e5, 1.2e-7 for
@@ -421,11 +478,13 @@ struct FwdArgs {
   float* v; float* theta; float* total; float* last;
   float* ckpt;             // [nbatch][K][(4+L)][N][G] or null
   float* pglob;            // [nbatch][K][G] or null
+  float* act;              // [nbatch][K][ActLayout.total] hidden activations for the backward pass, or null
   const uint16_t* topo;    // index block in global memory
   long long S;
   int N, Ns, E, Gn, K, NGQ, G, nbatch;   // Ns = bus slots (>= N)
   int NGs, EGs;            // padded row strides of the [.][Ns][G] and [.][E][G] arrays
   int need_grad;
+  ActLayout al;
   int use_tma;             // inputs 16-byte aligned and staging present: prefetch the next batch with cp.async.bulk
   unsigned char grp_of_warp[32];   // warp -> group of 32/NGQ consecutive bus slots
   SmemPlan sm;

@@ -14,7 +14,7 @@
 
 namespace gns {
 
-template <int L, int H, bool MULTI, int VG, int TMAX>
+template <int L, int H, bool MULTI, int VG, int TMAX, bool GRAD>
 __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   constexpr WLayout W = make_wlayout(L, H, MULTI);
   constexpr int HP = pad4(H);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         for (int i = tid; i < W.wstep / 4; i += T) dst[i] = __ldg(src + i);
       }
       // ---------------- checkpoint: state entering step k (k >= 1) ----------------
-      if (a.need_grad && k >= 1) {
+      if (GRAD && k >= 1) {
         const int nst4 = (4 + L) * NG / 4;
         float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (k - 1)) * (size_t)((4 + L) * NG));
         const float4* srcs = reinterpret_cast<const float4*>(s_state);
@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       // ---------------- bus phase: phi nets, aggregation, L nets ----------------
       {
         const int n = pslot;                         // the bus's state lives in its primary slot
+        // training: hidden activations of this step for the backward kernel (see ActLayout)
+        float* const act_k = GRAD ? a.act + ((size_t)batch * K + k) * (size_t)a.al.total : nullptr;
         float* st = s_state + n * G + gcol;
         const float* sm_m = st + 4 * NG;
         const float degf = (float)(e_full1 - e_in0); // in-degree of the bus (primary)
@@ -339,7 +341,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
               for (int o = 0; o < H; ++o)
 #pragma unroll
-                for (int g = 0; g < VG; ++g) A[o][g] += lrelu(z2[o][g]);
+                for (int g = 0; g < VG; ++g) { z2[o][g] = lrelu(z2[o][g]); A[o][g] += z2[o][g]; }
+              if constexpr (GRAD) {
+                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * EG + e * G + gcol;
+#pragma unroll
+                for (int o = 0; o < H; ++o) { stg_stream<VG>(ap + o * EG, z[o]); stg_stream<VG>(ap + (H + o) * EG, z2[o]); }
+              }
             }
            }
             if (warp_has_twins) {   // twins: combine the partial aggregates of a bus (lanes NGQ apart)
@@ -356,6 +363,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             }
           }
           if (!prim) continue;
+          float* const ab = GRAD ? act_k + (size_t)(q * 3 * H) * NG + n * G + gcol : nullptr;
+          if constexpr (GRAD) {
+#pragma unroll
+            for (int o = 0; o < H; ++o) stg_stream<VG>(ab + o * NG, A[o]);
+          }
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
           float zL[H][VG];
           {
@@ -404,6 +416,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
           for (int o = 0; o < H; ++o)
 #pragma unroll
             for (int g = 0; g < VG; ++g) z2[o][g] = lrelu(z2[o][g]);
+          if constexpr (GRAD) {
+#pragma unroll
+            for (int o = 0; o < H; ++o) { stg_stream<VG>(ab + (H + o) * NG, zL[o]); stg_stream<VG>(ab + (2 * H + o) * NG, z2[o]); }
+          }
           if (q < 2) {
             float out[VG];
             const float bo = wln[W.ln_bo_s];
@@ -540,7 +556,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         lam[g] = (pglob < sPset[g]) ? l1 : l2;
         lo_arm[g] = lam[g] < 0.5f;
       }
-      if (a.need_grad && tid < NGQ) IO::st(a.pglob + ((size_t)batch * K + k) * G + gcol, pj);
+      if (GRAD && tid < NGQ) IO::st(a.pglob + ((size_t)batch * K + k) * G + gcol, pj);
       if (bus_on) {
         const int n = slot;
         float pgs[VG];
@@ -601,7 +617,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     }  // k
 
     // ---------------- outputs ----------------
-    if (a.need_grad) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
+    if (GRAD) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
       const int nst4 = (4 + L) * NG / 4;
       float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)((4 + L) * NG));
       const float4* srcs = reinterpret_cast<const float4*>(s_state);

@@ -30,6 +30,8 @@ struct gns_plan {
   // canonical(state_dict order) -> packed index maps, cached per (K,L,H,multi)
   struct PackMap { int32_t* d_map = nullptr; int64_t n_canon = 0; int64_t n_packed = 0; };
   std::map<std::tuple<int, int, int, int>, PackMap> pack_maps;
+  // packed index -> fragment-order accumulator index (device), cached per (L,H,multi)
+  std::map<std::tuple<int, int, int>, int32_t*> frag_maps;
 };
 
 namespace gns {
@@ -52,7 +54,8 @@ struct Workspace {
   size_t packed_params = 0;   // [K][wstep] floats
   size_t ckpt = 0;            // [nbatch][K][pad4((4+L) N G)] floats   (need_grad)
   size_t pglob = 0;           // [nbatch][K][G] floats                 (need_grad)
-  size_t gpartial = 0;        // [ctas][K][wstep] floats               (need_grad): per-CTA gradient partial sums
+  size_t act = 0;             // [nbatch][K][ActLayout.total] floats   (need_grad): hidden activations
+  size_t gpartial = 0;        // [ctas*nwarps][K][FragLayout.step] floats (need_grad): per-warp gradient partial sums
   size_t packed_grad = 0;     // [K][wstep] floats                     (need_grad)
   size_t mscratch = 0;        // [ctas][2][L][NGs] floats              (need_grad, L > 32)
   size_t total = 0;

@@ -7,9 +7,9 @@
 
 namespace gns {
 
-template <int L, int H, bool MULTI, int VG, int TMAX>
-static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
-  auto kern = gns_forward_kernel<L, H, MULTI, VG, TMAX>;
+template <int L, int H, bool MULTI, int VG, int TMAX, bool GRAD>
+static cudaError_t launch_forward_g(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
+  auto kern = gns_forward_kernel<L, H, MULTI, VG, TMAX, GRAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -19,6 +19,13 @@ static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStrea
   const int ctas = std::min(g.nbatch, occ * g.num_sms);
   kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+// the training variant (GRAD) also writes the state and activation checkpoints
+template <int L, int H, bool MULTI, int VG, int TMAX>
+static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
+  return a.need_grad ? launch_forward_g<L, H, MULTI, VG, TMAX, true>(a, g, st)
+                     : launch_forward_g<L, H, MULTI, VG, TMAX, false>(a, g, st);
 }
 
 template <int L, int H>

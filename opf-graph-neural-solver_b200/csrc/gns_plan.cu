@@ -273,7 +273,9 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     const size_t nst = (size_t)(4 + md.L) * row_stride(plan->Ns * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
-    w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * W.wstep * 4);   // one block per warp
+    const ActLayout al = make_act_layout(md.H, md.multi ? 3 : 1, row_stride(plan->Ns * fwd.G), row_stride(plan->E * fwd.G));
+    w.act = o; o = align(o + (size_t)fwd.nbatch * md.K * (size_t)al.total * 4);
+    w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * make_frag_layout(md.L, md.H).step * 4);   // one block per warp
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
     if (md.L > 32) { w.mscratch = o; o = align(o + (size_t)bwd.ctas * 2 * md.L * row_stride(plan->Ns * bwd.G) * 4); }
   }
@@ -431,6 +433,7 @@ extern "C" void gns_plan_destroy(gns_plan* p) {
   if (p->d_expect) cudaFree(p->d_expect);
   if (p->d_flag) cudaFree(p->d_flag);
   for (auto& kv : p->pack_maps) if (kv.second.d_map) cudaFree(kv.second.d_map);
+  for (auto& kv : p->frag_maps) if (kv.second) cudaFree(kv.second);
   delete p;
 }
 
