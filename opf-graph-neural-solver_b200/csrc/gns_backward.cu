@@ -44,7 +44,7 @@ std::vector<int32_t> build_frag_map(const ModelDims& md) {
     }
     const int lb = W.off_ln[0] + q * W.ln_size_s;
     if (q < 2) {
-      for (int r = 0; r < H + 1; ++r) put(lb + (r < H ? W.ln_wo + r : W.ln_bo_s), fb + F.out + r);
+      for (int r = 0; r < H + 1; ++r) put(lb + (r < H ? W.ln_wo + r : W.ln_bo_s), fb + F.out + frag_index(r, 0));
     } else {
       for (int r = 0; r < L; ++r)
         for (int c = 0; c < H + 1; ++c) put(lb + (c < H ? W.ln_wo + r * W.HP + c : W.ln_bo_m + r), fb + F.out + frag_index(r, c));

@@ -9,11 +9,12 @@
 //      back-propagates them (dX), mirroring the bus-centric forward.  Nothing is recomputed.
 //   3. weight gradients (the only GEMM-shaped work): dW^T[w][o] = sum_items wide[w] * hid[o].
 //      Each warp transposes the per-item vectors of its 32 items through a private shared
-//      memory tile ([feature][item]); lane r then owns row r of dW^T and runs over the 32
-//      items with 128-bit loads (the hid rows are warp-uniform broadcasts).  State rows
-//      (v, theta, dP, dQ, m, adj m) are already stored [feature][item] and are read in place.
-//      Row sums go to a per-warp private accumulator in global memory (plain RMW, L2
-//      resident), reduced over warps by a second small kernel: deterministic, no atomics.
+//      memory tile and runs the 32-item product on the tensor cores (mma.sync m16n8k8 TF32 with
+//      a 3-term split that keeps FP32 accuracy).  State rows (v, theta, dP, dQ, m, adj m) are
+//      already stored [feature][item] and are read in place as B fragments.  The accumulator
+//      cells go to a per-warp private block in global memory in fragment order (one 128-bit
+//      reduction per lane and 8-row tile, L2 resident), summed over warps and re-ordered by a
+//      second small kernel: deterministic, no contended atomics.
 #pragma once
 #include "gns_common.cuh"
 
@@ -21,12 +22,6 @@ namespace gns {
 
 #ifndef GNS_BWD_L2PREFETCH
 #define GNS_BWD_L2PREFETCH 1
-#endif
-#ifndef GNS_TG_SPLIT
-#define GNS_TG_SPLIT 1
-#endif
-#ifndef GNS_TG_PREFETCH
-#define GNS_TG_PREFETCH 1
 #endif
 #ifndef GNS_KTS
 #define GNS_KTS 48
@@ -38,12 +33,20 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
   int nxt;                // [4][NGs]      v', theta', dP', dQ' of the state leaving the step
   int lineg;              // [5][EGs]      per-line partials: d/dv_f, d/dv_t, d/dtheta_f, d/dD_A, d/dD_B
   int adjD;               // [NGs]         adjoint of the alias-line angle differences
-  int tiles;              // [nwarps][trows][kTS]
-  int trows;
+  int tiles;              // [nwarps][tfloats]
+  int tfloats;
   int total;
 };
 
-__host__ __device__ inline int bwd_tile_rows(int H, int /*PO*/) { return 1 + (H + 1) + 16 + (H + 1); }
+// Per-warp tile (floats): [ones row][hid block A][16 wide rows][S rows | hid block B].
+// Wide rows are [row][item] with stride kTS.  A hid block holds the hidden-side vectors of the 32 items
+// interleaved for the MMA A fragment: [pair p = c % 8][item][c / 8] with row stride kSA, so one LDS.128 at
+// item a yields {c[a], c+8[a], c[a+1], c+8[a+1]} = (a0, a1, a2, a3) of an m16n8k8 with k slots (t, t+4) =
+// items (a, a+1): no register shuffling in front of the HMMA.
+constexpr int kSA = 68;   // 64 + 4: the 8 lanes of a 128-bit phase (2 pair rows x 4 quads 8 floats apart) hit 32 distinct banks
+__host__ __device__ constexpr int bwd_hid_floats() { return 8 * kSA; }
+__host__ __device__ constexpr int bwd_srows_floats(int H) { return (H + 1) * kTS > bwd_hid_floats() ? (H + 1) * kTS : bwd_hid_floats(); }
+__host__ __device__ constexpr int bwd_tile_floats(int H) { return kTS + bwd_hid_floats() + 16 * kTS + bwd_srows_floats(H); }
 
 __host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps,
                                                 bool mglobal = false) {
@@ -54,8 +57,9 @@ __host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int
   b.nxt = o; o += 4 * NGs;
   b.lineg = o; o += 5 * EGs;
   b.adjD = o; o += NGs;
-  b.trows = bwd_tile_rows(H, PO);
-  b.tiles = o; o += nwarps * b.trows * kTS;
+  (void)PO;
+  b.tfloats = bwd_tile_floats(H);
+  b.tiles = o; o += nwarps * b.tfloats;
   b.total = o;
   return b;
 }
@@ -81,67 +85,6 @@ struct BwdArgs {
   TopoOffsets to;
   float wk[kMaxK];
 };
-
-// dW^T[r][c] += sum_{item<32} row_r[item] * hid_c[item]   for rows r in [rb, re).
-// rowfn(r) -> pointer to 32 consecutive floats (16-byte aligned); hid rows are kTS apart;
-// outfn(r, c) -> offset inside this warp's private accumulator block.
-// PARTS lanes share one row, each running over 32/PARTS items, and are folded by shuffles: a
-// chunk of <= 8 (<= 16) rows keeps 32 lanes busy with 4 (2) item parts instead of idling 24 (16).
-template <int C, int PARTS, class RowFn, class OutFn>
-__device__ __forceinline__ void tile_gemm_chunk(int rb, int re, RowFn rowfn, const float* __restrict__ hid,
-                                                float* __restrict__ g, OutFn outfn) {
-  constexpr int RW = 32 / PARTS;          // rows per pass
-  constexpr int QP = 8 / PARTS;           // item quads per part
-  const int lane = threadIdx.x & 31;
-  const int part = lane / RW;
-  for (int r0 = rb; r0 < re; r0 += RW) {
-    const int r = r0 + (lane % RW);
-    const bool on = r < re;
-    const float4* a4 = reinterpret_cast<const float4*>(rowfn(on ? r : rb)) + part * QP;
-    const float* h0 = hid + 4 * part * QP;
-    const bool writer = on && part == 0;
-    float acc[C];
-#if GNS_TG_PREFETCH
-    float old[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) old[c] = writer ? g[outfn(r, c)] : 0.f;
-#endif
-#pragma unroll
-    float2 acc2[C];                      // item pairs per column: FFMA2, folded at the end
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc2[c] = make_float2(0.f, 0.f);
-#pragma unroll 2
-    for (int q = 0; q < QP; ++q) {
-      const float4 av = a4[q];
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float4 h = *reinterpret_cast<const float4*>(h0 + c * kTS + 4 * q);
-        acc2[c] = fma2(make_float2(av.x, av.y), make_float2(h.x, h.y), acc2[c]);
-        acc2[c] = fma2(make_float2(av.z, av.w), make_float2(h.z, h.w), acc2[c]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = acc2[c].x + acc2[c].y;
-    if (PARTS > 1) {
-#pragma unroll
-      for (int d = RW; d < 32; d *= 2) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
-      }
-    }
-    if (writer) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-#if GNS_TG_PREFETCH
-        g[outfn(r, c)] = old[c] + acc[c];
-#else
-        float* p = g + outfn(r, c);
-        *p += acc[c];
-#endif
-      }
-    }
-  }
-}
 
 // ---- weight-gradient tiles on the tensor cores: mma.sync m16n8k8 TF32 with a 3-term split ----
 // D[hid c][wide r] += sum_item hid_c[item] * row_r[item]: M = hidden columns (C <= 16), N = 8 wide rows per
@@ -169,27 +112,21 @@ __device__ __forceinline__ void red_add_v4(float* p, const float (&d)[4]) {   //
 // gfrag: this call's block of the warp-private accumulator (FragLayout); only this warp ever adds to it,
 // in program order, so the reductions are deterministic.
 template <int C, int R, class RowFn>
-__device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hid, float* __restrict__ gfrag) {
+__device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
   static_assert(C <= 16, "hidden side must fit one m16 tile");
   const int lane = threadIdx.x & 31, gi = lane >> 2, t = lane & 3;
-  // A fragments (hidden columns gi and gi+8) for the four MMAs of the 32 items
-  uint32_t ab[4][4], as[4][4];            // [mma i][a0..a3], big and small parts
-  {
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* h0 = hid + gi * kTS + 4 * t;
-    const float* h1 = hid + (gi + 8) * kTS + 4 * t;
-    const float4 lo0 = (gi < C) ? *reinterpret_cast<const float4*>(h0) : z4;
-    const float4 hi0 = (gi < C) ? *reinterpret_cast<const float4*>(h0 + 16) : z4;
-    const float4 lo1 = (C > 8 && gi + 8 < C) ? *reinterpret_cast<const float4*>(h1) : z4;
-    const float4 hi1 = (C > 8 && gi + 8 < C) ? *reinterpret_cast<const float4*>(h1 + 16) : z4;
-    const float l0[4] = {lo0.x, lo0.y, lo0.z, lo0.w}, u0[4] = {hi0.x, hi0.y, hi0.z, hi0.w};
-    const float l1[4] = {lo1.x, lo1.y, lo1.z, lo1.w}, u1[4] = {hi1.x, hi1.y, hi1.z, hi1.w};
+  // A fragments of the four MMAs: MMA m covers items a(t, m) = 16 (m / 2) + 4 t + 2 (m % 2) and a + 1
+  uint32_t ab[4][4], as[4][4];            // [mma][a0..a3], big and small parts
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      split_tf32(l0[i], ab[i][0], as[i][0]);
-      split_tf32(l1[i], ab[i][1], as[i][1]);
-      split_tf32(u0[i], ab[i][2], as[i][2]);
-      split_tf32(u1[i], ab[i][3], as[i][3]);
+  for (int m = 0; m < 4; ++m) {
+    const float4 q = *reinterpret_cast<const float4*>(hidblk + gi * kSA + 2 * ((m >> 1) * 16 + 4 * t + (m & 1) * 2));
+    split_tf32(q.x, ab[m][0], as[m][0]);
+    split_tf32(q.z, ab[m][2], as[m][2]);
+    if (C > 8) {
+      split_tf32(q.y, ab[m][1], as[m][1]);
+      split_tf32(q.w, ab[m][3], as[m][3]);
+    } else {
+      ab[m][1] = as[m][1] = ab[m][3] = as[m][3] = 0u;
     }
   }
   constexpr int NT = (R + 7) / 8;
@@ -201,22 +138,22 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
     float4 blo = *reinterpret_cast<const float4*>(rp);
     float4 bhi = *reinterpret_cast<const float4*>(rp + 16);
     if (!rv) { blo = make_float4(0.f, 0.f, 0.f, 0.f); bhi = blo; }
-    const float bl[4] = {blo.x, blo.y, blo.z, blo.w}, bu[4] = {bhi.x, bhi.y, bhi.z, bhi.w};
-    uint32_t bb0[4], bs0[4], bb1[4], bs1[4];
-    float di[2][4];                       // two accumulator chains: consecutive MMAs are independent
+    const float bv[4][2] = {{blo.x, blo.y}, {blo.z, blo.w}, {bhi.x, bhi.y}, {bhi.z, bhi.w}};
+    uint32_t bb[4][2], bs[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      split_tf32(bl[i], bb0[i], bs0[i]);
-      split_tf32(bu[i], bb1[i], bs1[i]);
+    for (int m = 0; m < 4; ++m) {
+      split_tf32(bv[m][0], bb[m][0], bs[m][0]);
+      split_tf32(bv[m][1], bb[m][1], bs[m][1]);
     }
+    float di[2][4];                       // two accumulator chains
 #pragma unroll
     for (int j = 0; j < 4; ++j) { di[0][j] = 0.f; di[1][j] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mma_tf32(di[i & 1], as[i], bb0[i], bb1[i]);
+    for (int m = 0; m < 4; ++m) mma_tf32(di[m & 1], as[m], bb[m][0], bb[m][1]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mma_tf32(di[i & 1], ab[i], bs0[i], bs1[i]);
+    for (int m = 0; m < 4; ++m) mma_tf32(di[m & 1], ab[m], bs[m][0], bs[m][1]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mma_tf32(di[i & 1], ab[i], bb0[i], bb1[i]);
+    for (int m = 0; m < 4; ++m) mma_tf32(di[m & 1], ab[m], bb[m][0], bb[m][1]);
     float d[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) d[j] = di[0][j] + di[1][j];
@@ -224,22 +161,11 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
   }
 }
 
-#ifndef GNS_TG_MMA
-#define GNS_TG_MMA 1
-#endif
-
 // one weight-gradient GEMM call: rows r < R (wide side) x C hidden columns over the warp's 32 items, added
-// into the call's accumulator block.  C == 1 (output layer of the scalar nets) keeps the lane-per-row
-// FFMA form and stores cell r at gfrag[r].
+// into the call's accumulator block
 template <int C, int R, class RowFn>
-__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hid, float* __restrict__ gfrag) {
-  if constexpr (C > 1) {
-    tile_gemm_mma<C, R>(rowfn, hid, gfrag);
-  } else {
-    static_assert(R <= 16, "scalar path");
-    constexpr int P = GNS_TG_SPLIT ? (R <= 8 ? 4 : 2) : 1;
-    tile_gemm_chunk<C, P>(0, R, rowfn, hid, gfrag, [](int r, int) { return r; });
-  }
+__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
+  tile_gemm_mma<C, R>(rowfn, hidblk, gfrag);
 }
 
 // Large latent dimensions (L > 32): state m and its adjoint (2 x L x Ns floats, 183 KB for L=64 on
@@ -253,12 +179,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   constexpr FragLayout FL = make_frag_layout(L, H);
   constexpr int HP = pad4(H);
   // tile row map
-  constexpr int R_ONES = 0;
-  constexpr int R_HID = 1;                 // H+1 rows
-  constexpr int R_WIDE = R_HID + H + 1;    // 16 rows
-  constexpr int R_S = R_WIDE + 16;         // H+1 rows: the aggregate A and the in-degree (wide rows of dM / dc) ...
-  constexpr int R_HID2 = R_S;              // ... and, once those are dead (phi adjoint), a second hid block
-  static_assert(H + 1 + 5 <= 16, "wide staging rows");
+  constexpr int T_ONES = 0;                              // wide row of ones (bias gradients)
+  constexpr int T_HIDA = kTS;                            // hid block A
+  constexpr int T_WIDE = T_HIDA + bwd_hid_floats();      // 16 wide rows
+  constexpr int T_S = T_WIDE + 16 * kTS;                 // H+1 wide rows: the aggregate A and the in-degree (rows of dM / dc) ...
+  constexpr int T_HIDB = T_S;                            // ... and, once those are dead (phi adjoint), hid block B
+  static_assert(H + 1 + 5 <= 16 && H + 1 <= 16, "wide staging rows / one m16 tile");
 
   extern __shared__ __align__(16) float smem[];
   const int N = a.N, E = a.E, Gn = a.Gn, G = a.G, NGQ = a.NGQ, K = a.K;
@@ -286,7 +212,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const int slot = grp * (32 / NGQ) + lane / NGQ;
   const int gq = lane % NGQ;
   const bool slot_on = slot < a.Ns;           // owns a bus slot (primary or twin)
-  float* const tile = smem + a.sm.extra + a.bs.tiles + warp * a.bs.trows * kTS;
+  float* const tile = smem + a.sm.extra + a.bs.tiles + warp * a.bs.tfloats;
   float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * FL.step);
 
   // zero all dynamic shared memory once: padding lanes and tail rows must hold finite values
@@ -294,7 +220,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   __syncthreads();
   for (int i = tid; i < a.to.total / 2; i += T)
     reinterpret_cast<uint32_t*>(s_topo)[i] = reinterpret_cast<const uint32_t*>(a.topo)[i];
-  tile[R_ONES * kTS + lane] = 1.f;
+  tile[T_ONES + lane] = 1.f;
   const uint16_t* const t_fi = s_topo + a.to.fi;
   const uint16_t* const t_ti = s_topo + a.to.ti;
   const uint16_t* const t_fa = s_topo + a.to.fa;
@@ -333,7 +259,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const bool is_gen = j1 > j0;
   const int warp_max_deg = __reduce_max_sync(0xffffffffu, deg);
 
-  auto stage = [&](int row, float val) { tile[row * kTS + lane] = bus_on ? val : 0.f; };
+  auto stage = [&](int off, int row, float val) { tile[off + row * kTS + lane] = bus_on ? val : 0.f; };          // wide row
+  auto stage_hid = [&](int blk, int c, float val) { tile[blk + (c & 7) * kSA + lane * 2 + (c >> 3)] = bus_on ? val : 0.f; };
 
   for (int batch = blockIdx.x; batch < a.nbatch; batch += gridDim.x) {
     const long long g0 = (long long)batch * G;
@@ -576,18 +503,17 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             __syncwarp();
 #pragma unroll
             for (int o = 0; o < H; ++o) {
-              tile[(R_HID + o) * kTS + lane] = d2[o][0];
-              tile[(R_HID2 + o) * kTS + lane] = d1[o];
-              tile[(R_WIDE + o) * kTS + lane] = live ? h1[o] : 0.f;
+              tile[T_HIDA + (o & 7) * kSA + lane * 2 + (o >> 3)] = d2[o][0];
+              tile[T_HIDB + (o & 7) * kSA + lane * 2 + (o >> 3)] = d1[o];
+              tile[T_WIDE + o * kTS + lane] = live ? h1[o] : 0.f;
             }
 #pragma unroll
-            for (int c = 0; c < 5; ++c) tile[(R_WIDE + H + 1 + c) * kTS + lane] = live ? feat[c] : 0.f;
+            for (int c = 0; c < 5; ++c) tile[T_WIDE + (H + 1 + c) * kTS + lane] = live ? feat[c] : 0.f;
             __syncwarp();
             // dW2^T[j][o] += h1[j] d2[o];  db2[o] += d2[o]
-            tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
-                         tile + R_HID * kTS, gphi + FL.w2l);
+            tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? T_WIDE + r * kTS : T_ONES); }, tile + T_HIDA, gphi + FL.w2l);
             // dW1f^T[c5][o] += feat[c5] d1[o]
-            tile_gemm_r<H, 5>([&](int r) { return tile + (R_WIDE + H + 1 + r) * kTS; }, tile + R_HID2 * kTS, gphi + FL.w1f);
+            tile_gemm_r<H, 5>([&](int r) { return tile + T_WIDE + (H + 1 + r) * kTS; }, tile + T_HIDB, gphi + FL.w1f);
           }
           if (warp_has_twins) {   // the bus owner needs the sum over its twins
 #pragma unroll
@@ -601,11 +527,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           }
           __syncwarp();
 #pragma unroll
-          for (int o = 0; o < H; ++o) stage(R_HID + o, adjP[o]);
+          for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, adjP[o]);
           __syncwarp();
           // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
-          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * NG : tile + R_ONES * kTS; },
-                       tile + R_HID * kTS, gphi + FL.w1m);
+          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * NG : tile + T_ONES; }, tile + T_HIDA, gphi + FL.w1m);
           {
             float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
 #pragma unroll 4
@@ -635,8 +560,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             for (int o = 0; o < H; ++o) { Aq[o] = __ldg(ab + o * NGf); h1L[o] = __ldg(ab + (H + o) * NGf); h2L[o] = __ldg(ab + (2 * H + o) * NGf); }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < H; ++j) stage(R_S + j, Aq[j]);       // wide rows of dM
-            stage(R_S + H, degf);                                    // wide row of dc
+            for (int j = 0; j < H; ++j) stage(T_S, j, Aq[j]);        // wide rows of dM
+            stage(T_S, H, degf);                                     // wide row of dc
           }
 
           // ---- output layer adjoint and its weight gradient ----
@@ -648,12 +573,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             float gv[1] = {g};
             row_axpy<H, HP, 1>(dh2, gv, wln + W.ln_wo);
 #pragma unroll
-            for (int o = 0; o < H; ++o) stage(R_WIDE + o, h2L[o]);
-            stage(R_HID, g);
+            for (int o = 0; o < H; ++o) stage(T_WIDE, o, h2L[o]);
+            stage_hid(T_HIDA, 0, g);
             __syncwarp();
             // dWout[j] += g h2[j];  dbout += g      (rows = [h2 (H), ones], one column g)
-            tile_gemm_r<1, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
-                         tile + R_HID * kTS, gln + FL.out);
+            tile_gemm_r<1, H + 1>([&](int r) { return tile + (r < H ? T_WIDE + r * kTS : T_ONES); }, tile + T_HIDA, gln + FL.out);
           } else {
 #pragma unroll 2
             for (int i = 0; i < L; ++i) {
@@ -661,11 +585,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
               row_axpy<H, HP, 1>(dh2, gm, wln + W.ln_wo + i * HP);
             }
 #pragma unroll
-            for (int o = 0; o < H; ++o) stage(R_HID + o, h2L[o]);
-            stage(R_HID + H, 1.f);
+            for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, h2L[o]);
+            stage_hid(T_HIDA, H, 1.f);
             __syncwarp();
             // dWout[i][j] += adjm'[i] h2[j];  dbout[i] += adjm'[i]    (rows = adj m' rows in place)
-            tile_gemm_r<H + 1, L>([&](int r) { return rows_am + r * NG; }, tile + R_HID * kTS, gln + FL.out);
+            tile_gemm_r<H + 1, L>([&](int r) { return rows_am + r * NG; }, tile + T_HIDA, gln + FL.out);
           }
           __syncwarp();
           // ---- second layer ----
@@ -673,12 +597,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
           for (int o = 0; o < H; ++o) {
             d2[o][0] = dh2[o][0] * lrelu_grad(h2L[o]);
-            stage(R_HID + o, d2[o][0]);
-            stage(R_WIDE + o, h1L[o]);
+            stage_hid(T_HIDA, o, d2[o][0]);
+            stage(T_WIDE, o, h1L[o]);
           }
           __syncwarp();
-          tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? (R_WIDE + r) : R_ONES) * kTS; },
-                       tile + R_HID * kTS, gln + FL.w2);
+          tile_gemm_r<H, H + 1>([&](int r) { return tile + (r < H ? T_WIDE + r * kTS : T_ONES); }, tile + T_HIDA, gln + FL.w2);
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             float t[1] = {0.f};
@@ -688,16 +611,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           __syncwarp();
           // ---- first layer: dW1^T[i][o] += x[i] d1[o] with x = [v,theta,dP,dQ, m, S], db1 += d1 ----
 #pragma unroll
-          for (int o = 0; o < H; ++o) stage(R_HID + o, d1[o][0]);
+          for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, d1[o][0]);
           __syncwarp();
           // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
           tile_gemm_r<H, 4 + L + H + 2>(
               [&](int r) {
                 return r < 4 ? rows_state + r * NG
                        : r < 4 + L ? rows_m + (r - 4) * NG
-                                 : (r < 4 + L + H + 1 ? tile + (R_S + r - 4 - L) * kTS : tile + R_ONES * kTS);
+                                 : (r < 4 + L + H + 1 ? tile + T_S + (r - 4 - L) * kTS : tile + T_ONES);
               },
-              tile + R_HID * kTS, gln + FL.w1);
+              tile + T_HIDA, gln + FL.w1);
           __syncwarp();
           // ---- dX of the first layer ----
 #pragma unroll
