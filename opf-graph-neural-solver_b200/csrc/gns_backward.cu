@@ -191,7 +191,7 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.gacc = gacc;
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
-  a.NGs = row_stride(plan->Ns * gb.G); a.EGs = row_stride(plan->E * gb.G);
+  a.NGs = bwd_bus_stride(plan->Ns * gb.G); a.EGs = row_stride(plan->E * gb.G);
   a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G); a.EGs_f = row_stride(plan->E * gf.G);
   a.al = make_act_layout(md.H, md.multi ? 3 : 1, a.NGs_f, a.EGs_f);
   std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);

@@ -35,6 +35,7 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
   int adjD;               // [NGs]         adjoint of the alias-line angle differences
   int tiles;              // [nwarps][tfloats]
   int tfloats;
+  int mbar;               // 8-byte mbarrier of the per-step weight copy
   int total;
 };
 
@@ -51,7 +52,7 @@ __host__ __device__ constexpr int bwd_tile_floats(int H) { return kTS + bwd_hid_
 __host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int H, int PO, int nwarps,
                                                 bool mglobal = false) {
   BwdSmem b{};
-  const int NGs = row_stride(N * G), EGs = row_stride(E * G);
+  const int NGs = bwd_bus_stride(N * G), EGs = row_stride(E * G);
   int o = 0;
   b.adj = o; o += (mglobal ? 4 : 4 + L) * NGs;   // large latent: m / adj m rows live in a global scratch instead
   b.nxt = o; o += 4 * NGs;
@@ -60,6 +61,7 @@ __host__ __device__ inline BwdSmem make_bwd_smem(int N, int E, int G, int L, int
   (void)PO;
   b.tfloats = bwd_tile_floats(H);
   b.tiles = o; o += nwarps * b.tfloats;
+  b.mbar = o; o += 4;
   b.total = o;
   return b;
 }
@@ -130,7 +132,8 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
     }
   }
   constexpr int NT = (R + 7) / 8;
-#pragma unroll
+  constexpr int UNR = NT <= 5 ? NT : 1;   // long tiles (latent_dim 64) stay rolled: unrolling them only buys spills
+#pragma unroll UNR
   for (int nt = 0; nt < NT; ++nt) {
     const int row = nt * 8 + gi;
     const bool rv = (nt * 8 + 8 <= R) || (row < R);
@@ -221,6 +224,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   for (int i = tid; i < a.to.total / 2; i += T)
     reinterpret_cast<uint32_t*>(s_topo)[i] = reinterpret_cast<const uint32_t*>(a.topo)[i];
   tile[T_ONES + lane] = 1.f;
+  // per-step weights arrive by one bulk copy (cp.async.bulk + mbarrier) issued as soon as the previous
+  // step's MLP phase is over, so the copy runs under the physics adjoint instead of in front of it
+  uint64_t* const s_mbar = reinterpret_cast<uint64_t*>(smem + a.sm.extra + a.bs.mbar);
+  uint32_t w_phase = 0;
+  auto weights_issue = [&](int k) {   // one thread, after a block barrier that follows the last read of s_w
+    fence_proxy_async();
+    mbar_expect_tx(s_mbar, W.wstep * 4);
+    bulk_g2s(s_w, a.params + (size_t)k * W.wstep, W.wstep * 4, s_mbar);
+  };
   const uint16_t* const t_fi = s_topo + a.to.fi;
   const uint16_t* const t_ti = s_topo + a.to.ti;
   const uint16_t* const t_fa = s_topo + a.to.fa;
@@ -239,7 +251,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const uint16_t* const t_rank = s_topo + a.to.rank_of;
   const uint16_t* const t_prim = s_topo + a.to.prim_of;
   const uint16_t* const t_gsz = s_topo + a.to.gsz;
+  if (tid == 0) { mbar_init(s_mbar, 1); fence_proxy_async(); }
   __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < a.nbatch) weights_issue(K - 1);
 
   // slot bookkeeping: a bus's state / adjoint live in its primary slot; twins only help with its lines
   const int sl = slot_on ? slot : 0;
@@ -316,11 +330,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         for (int i = lane * 128; i < FL.step * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
       }
 #endif
-      {
-        const float4* src = reinterpret_cast<const float4*>(a.params + (size_t)k * W.wstep);
-        float4* dst = reinterpret_cast<float4*>(s_w);
-        for (int i = tid; i < W.wstep / 4; i += T) dst[i] = __ldg(src + i);
-      }
       if (bus_on) {
         if (k >= 1) {
           const float* ck = ck_base + (size_t)(k - 1) * ck_stride + (size_t)n * a.Gf;
@@ -456,6 +465,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int i = tid * 128; i < (int)(ck_stride * 4); i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
         }
       }
+      mbar_wait(s_mbar, w_phase);                      // this step's weights have landed
+      w_phase ^= 1;
       float* const gk = gacc_w + (size_t)k * FL.step;
       {
         float* adjrow = s_adj + nb;
@@ -470,6 +481,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         float adjA[H];
 #pragma unroll
         for (int o = 0; o < H; ++o) adjA[o] = 0.f;
+        // small latents: this step's additions to adj m stay in registers and are folded in once at the end
+        // (the only readers of adj m' inside the step, the m-net output layer and its tile, come first)
+        constexpr bool AMREG = (L <= 32);
+        float amr[AMREG ? L : 1];
+#pragma unroll
+        for (int i = 0; i < (AMREG ? L : 1); ++i) amr[i] = 0.f;
 
         // adjoint of one phi net given adjA: line loop, dW2 / db2 / dW1f, adjP, dW1m / db1, adj m
         auto phi_backward = [&](const float* wphi, float* gphi, const float* actl) {
@@ -533,11 +550,20 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * NG : tile + T_ONES; }, tile + T_HIDA, gphi + FL.w1m);
           {
             float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
+            if constexpr (AMREG) {
+#pragma unroll
+              for (int i = 0; i < L; ++i) {
+                float t[1] = {amr[i]};
+                row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
+                amr[i] = t[0];
+              }
+            } else {
 #pragma unroll 4
-            for (int i = 0; i < L; ++i) {
-              float t[1] = {0.f};
-              row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
-              if (bus_on) adjm[i * NG] += t[0];
+              for (int i = 0; i < L; ++i) {
+                float t[1] = {0.f};
+                row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
+                if (bus_on) adjm[i * NG] += t[0];
+              }
             }
           }
         };
@@ -629,11 +655,20 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + i * HP);
             adj4[i] += t[0];
           }
+          if constexpr (AMREG) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+              float t[1] = {amr[i]};
+              row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
+              amr[i] = t[0];
+            }
+          } else {
 #pragma unroll 4
-          for (int i = 0; i < L; ++i) {
-            float t[1] = {0.f};
-            row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
-            if (bus_on) adjm[i * NG] += t[0];
+            for (int i = 0; i < L; ++i) {
+              float t[1] = {0.f};
+              row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
+              if (bus_on) adjm[i * NG] += t[0];
+            }
           }
           if (MULTI) {
 #pragma unroll
@@ -649,6 +684,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           if (MULTI || qq == 2)
             phi_backward(wphi, gphi, act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * EGf);
         }
+        if constexpr (AMREG) {
+          if (bus_on) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) adjm[i * NG] += amr[i];
+          }
+        }
         if (bus_on) {
           adjrow[0 * NG] = adjv + adj4[0];
           adjrow[1 * NG] = adjth + adj4[1];
@@ -657,6 +698,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         }
       }
       __syncthreads();
+      if (tid == 0) {                                  // s_w is free: fetch the next step's weights (or the next batch's first)
+        if (k >= 1) weights_issue(k - 1);
+        else if (batch + (int)gridDim.x < a.nbatch) weights_issue(K - 1);
+      }
       // state_k's (v, theta, dP, dQ) are the primes of step k-1
       if (bus_on && k >= 1) {
 #pragma unroll

@@ -25,6 +25,14 @@ __host__ __device__ constexpr int row_stride(int items) {
   return ((p / 4) % 2 == 0) ? p + 4 : p;
 }
 
+// Backward kernel: per-bus rows double as MMA B operands ([feature][item], 128-bit loads by lanes
+// (row g, quad t)); a stride of 16 mod 32 floats puts the 8 lanes of every 128-bit phase on 32 distinct banks.
+__host__ __device__ constexpr int bwd_bus_stride(int items) {
+  int p = pad4(items);
+  while (p % 32 != 16) p += 4;
+  return p;
+}
+
 // ---------------------------------------------------------------------------------
 // Packed per-step weight layout.  Every matrix is stored [wide][HP]: the fast index is
 // always the hidden-side index (padded to a multiple of 4 for 128-bit broadcast loads),

@@ -48,7 +48,7 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
   SmemPlan s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
-  const int NGs = row_stride(N * G), EGs = row_stride(E * G);
+  const int NGs = backward ? bwd_bus_stride(N * G) : row_stride(N * G), EGs = row_stride(E * G);
   (void)L;
   s.state = take(state_rows * NGs);
   s.busc = take(4 * NGs);
@@ -277,7 +277,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     w.act = o; o = align(o + (size_t)fwd.nbatch * md.K * (size_t)al.total * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * make_frag_layout(md.L, md.H).step * 4);   // one block per warp
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
-    if (md.L > 32) { w.mscratch = o; o = align(o + (size_t)bwd.ctas * 2 * md.L * row_stride(plan->Ns * bwd.G) * 4); }
+    if (md.L > 32) { w.mscratch = o; o = align(o + (size_t)bwd.ctas * 2 * md.L * bwd_bus_stride(plan->Ns * bwd.G) * 4); }
   }
   w.total = o;
   return w;
