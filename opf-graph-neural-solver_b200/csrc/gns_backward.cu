@@ -1,6 +1,7 @@
 // gns_backward.cu — host side of the backward pass: geometry, launch, and the two small
 // kernels that fold the per-warp gradient accumulators into the state_dict-order gradient.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "gns_backward.cuh"
@@ -169,7 +170,11 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   const size_t per_part = (size_t)md.K * FL.step;
   const int32_t* d_inv = get_frag_map(plan, md);
   if (!d_inv) return -2;
-  const int nparts = gb.ctas * nwarps;
+  // GNS_DETERMINISTIC=0: the warps of a CTA share one accumulator block (10x smaller, L2 resident); the order of
+  // their floating-point reductions is then not fixed, so gradients are reproducible to rounding only
+  const char* det_env = std::getenv("GNS_DETERMINISTIC");
+  const bool per_warp = !(det_env && det_env[0] == '0');
+  const int nparts = gb.ctas * (per_warp ? nwarps : 1);
   float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
   float* packed_grad = reinterpret_cast<float*>(wsb + ws.packed_grad);
   cudaError_t e = cudaMemsetAsync(gacc, 0, (size_t)nparts * per_part * 4, st);
@@ -189,11 +194,12 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.act = reinterpret_cast<const float*>(wsb + ws.act);
   a.grad_total = grad_total; a.grad_last = grad_last; a.grad_v = grad_v; a.grad_theta = grad_theta;
   a.gacc = gacc;
+  a.acc_per_warp = per_warp ? 1 : 0;
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
   a.NGs = bwd_bus_stride(plan->Ns * gb.G); a.EGs = row_stride(plan->E * gb.G);
   a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G); a.EGs_f = row_stride(plan->E * gf.G);
-  a.al = make_act_layout(md.H, md.multi ? 3 : 1, a.NGs_f, a.EGs_f);
+  a.al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, gf.G);
   std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);
   a.sm = gb.sm;
   a.bs = make_bwd_smem(plan->Ns, plan->E, gb.G, md.L, md.H, md.L, nwarps, md.L > 32);

@@ -44,6 +44,9 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
 // interleaved for the MMA A fragment: [pair p = c % 8][item][c / 8] with row stride kSA, so one LDS.128 at
 // item a yields {c[a], c+8[a], c[a+1], c+8[a+1]} = (a0, a1, a2, a3) of an m16n8k8 with k slots (t, t+4) =
 // items (a, a+1): no register shuffling in front of the HMMA.
+#ifndef GNS_MMA_CHAINS
+#define GNS_MMA_CHAINS 2   // 2 vs 4 chains: identical time (measured), 2 saves registers
+#endif
 constexpr int kSA = 68;   // 64 + 4: the 8 lanes of a 128-bit phase (2 pair rows x 4 quads 8 floats apart) hit 32 distinct banks
 __host__ __device__ constexpr int bwd_hid_floats() { return 8 * kSA; }
 __host__ __device__ constexpr int bwd_srows_floats(int H) { return (H + 1) * kTS > bwd_hid_floats() ? (H + 1) * kTS : bwd_hid_floats(); }
@@ -79,6 +82,7 @@ struct BwdArgs {
   long long S;
   int N, Ns, E, Gn, K, NGQ, G, nbatch;
   int NGs, EGs;
+  int acc_per_warp;         // 1: one accumulator block per warp (bit-reproducible); 0: one per CTA, shared by its warps
   int Gf, NGs_f, EGs_f;     // forward geometry of the checkpoints
   ActLayout al;
   unsigned char grp_of_warp[32];
@@ -148,18 +152,24 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
       split_tf32(bv[m][0], bb[m][0], bs[m][0]);
       split_tf32(bv[m][1], bb[m][1], bs[m][1]);
     }
-    float di[2][4];                       // two accumulator chains
+    float di[GNS_MMA_CHAINS][4];          // independent accumulator chains (HMMA latency)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { di[0][j] = 0.f; di[1][j] = 0.f; }
+    for (int c = 0; c < GNS_MMA_CHAINS; ++c)
 #pragma unroll
-    for (int m = 0; m < 4; ++m) mma_tf32(di[m & 1], as[m], bb[m][0], bb[m][1]);
+      for (int j = 0; j < 4; ++j) di[c][j] = 0.f;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) mma_tf32(di[m & 1], ab[m], bs[m][0], bs[m][1]);
+    for (int m = 0; m < 4; ++m) mma_tf32(di[m % GNS_MMA_CHAINS], as[m], bb[m][0], bb[m][1]);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) mma_tf32(di[m & 1], ab[m], bb[m][0], bb[m][1]);
+    for (int m = 0; m < 4; ++m) mma_tf32(di[m % GNS_MMA_CHAINS], ab[m], bs[m][0], bs[m][1]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) mma_tf32(di[m % GNS_MMA_CHAINS], ab[m], bb[m][0], bb[m][1]);
     float d[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) d[j] = di[0][j] + di[1][j];
+    for (int j = 0; j < 4; ++j) {
+      d[j] = di[0][j];
+#pragma unroll
+      for (int c = 1; c < GNS_MMA_CHAINS; ++c) d[j] += di[c][j];
+    }
     red_add_v4(gfrag + nt * 128 + lane * 4, d);
   }
 }
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const int gq = lane % NGQ;
   const bool slot_on = slot < a.Ns;           // owns a bus slot (primary or twin)
   float* const tile = smem + a.sm.extra + a.bs.tiles + warp * a.bs.tfloats;
-  float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * FL.step);
+  float* const gacc_w = a.gacc + ((size_t)blockIdx.x * (a.acc_per_warp ? nwarps : 1) + (a.acc_per_warp ? warp : 0)) * ((size_t)K * FL.step);
 
   // zero all dynamic shared memory once: padding lanes and tail rows must hold finite values
   for (int i = tid; i < a.sm.total_floats; i += T) smem[i] = 0.f;
@@ -476,8 +486,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         const float* rows_m = m_rows + 32 * grp;
         const float* rows_am = am_rows + 32 * grp;
         // this grid's column of the activations the forward kernel kept for step k (no recompute here)
-        const float* const act_k = a.act + ((size_t)bf * K + k) * (size_t)a.al.total + cf;
-        const size_t NGf = (size_t)a.NGs_f, EGf = (size_t)a.EGs_f;
+        const float* const act_k = a.act + ((size_t)bf * K + k) * (size_t)a.al.total;
+        const size_t RB = (size_t)a.al.rb, RL = (size_t)a.al.rl;
         float adjA[H];
 #pragma unroll
         for (int o = 0; o < H; ++o) adjA[o] = 0.f;
@@ -501,10 +511,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             const bool live = slot_on && (it < deg);
             const float* wp = wphi + opaque_zero();
             const int e = live ? e_in0 + it : 0;                 // position in the in-list
-            const float* ap = actl + (size_t)e * a.Gf;
+            const float* ap = actl + e;
             float h1[H], h2[H], d2[H][1], d1[H], feat[5];
 #pragma unroll
-            for (int o = 0; o < H; ++o) { h1[o] = __ldg(ap + o * EGf); h2[o] = __ldg(ap + (H + o) * EGf); }
+            for (int o = 0; o < H; ++o) { h1[o] = __ldg(ap + o * RL); h2[o] = __ldg(ap + (H + o) * RL); }
             const float* lf = s_linef + (int)t_ini[e] * G + gq;
 #pragma unroll
             for (int c = 0; c < 5; ++c) feat[c] = lf[c * EG];
@@ -580,10 +590,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           // ---- activations of this bus and pair kept by the forward kernel: A, h1, h2 of the L-net ----
           float h1L[H], h2L[H];
           {
-            const float* ab = act_k + (size_t)(q * 3 * H) * NGf + (size_t)n * a.Gf;
+            const float* ab = act_k + (size_t)(q * 3 * H) * RB + (size_t)cf * a.al.nsp + n;
             float Aq[H];
 #pragma unroll
-            for (int o = 0; o < H; ++o) { Aq[o] = __ldg(ab + o * NGf); h1L[o] = __ldg(ab + (H + o) * NGf); h2L[o] = __ldg(ab + (2 * H + o) * NGf); }
+            for (int o = 0; o < H; ++o) { Aq[o] = __ldg(ab + o * RB); h1L[o] = __ldg(ab + (H + o) * RB); h2L[o] = __ldg(ab + (2 * H + o) * RB); }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < H; ++j) stage(T_S, j, Aq[j]);        // wide rows of dM
@@ -682,7 +692,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           }
           __syncwarp();
           if (MULTI || qq == 2)
-            phi_backward(wphi, gphi, act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * EGf);
+            phi_backward(wphi, gphi, act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * RL + (size_t)cf * a.al.esp);
         }
         if constexpr (AMREG) {
           if (bus_on) {

@@ -132,11 +132,16 @@ __host__ __device__ constexpr int frag_index(int r, int c) {
 // plan's in-list (each position is walked by exactly one slot).  172 floats per bus and step on
 // case300: 867 KB per grid for K=4, streamed once out and once in (~1.3 TB/s at 0.75 M grids/s).
 // ---------------------------------------------------------------------------------
-struct ActLayout { int line_off; int total; };
-__host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int NGs, int EGs) {
+// Rows are GRID-MAJOR, [row][grid][item] with every (row, grid) segment padded to a 128-byte multiple: the
+// backward kernel works on one grid per CTA, so its lanes read consecutive floats (every fetched sector
+// fully used); the forward kernel pays one 32-bit store per grid instead of one vector store.
+struct ActLayout { int nsp, esp, rb, rl, line_off, total; };
+__host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, int E, int G) {
   ActLayout a{};
-  a.line_off = 3 * 3 * H * NGs;
-  a.total = a.line_off + nphi * 2 * H * EGs;
+  a.nsp = (Ns + 31) & ~31; a.esp = (E + 31) & ~31;     // items per (row, grid) segment
+  a.rb = G * a.nsp; a.rl = G * a.esp;                    // row strides of the bus / line blocks
+  a.line_off = 3 * 3 * H * a.rb;
+  a.total = a.line_off + nphi * 2 * H * a.rl;
   return a;
 }
 
@@ -221,6 +226,11 @@ template <> __device__ __forceinline__ void stg_stream<2>(float* p, const float 
 }
 template <> __device__ __forceinline__ void stg_stream<4>(float* p, const float (&x)[4]) {
   __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
+}
+// one streaming 32-bit store per grid, `gstride` floats apart (grid-major activation rows)
+template <int VG> __device__ __forceinline__ void stg_grids(float* p, int gstride, const float (&x)[VG]) {
+#pragma unroll
+  for (int g = 0; g < VG; ++g) __stcs(p + g * gstride, x[g]);
 }
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }

@@ -14,6 +14,10 @@
 
 namespace gns {
 
+#ifndef GNS_GRAD_MREG
+#define GNS_GRAD_MREG 1   // training variant: keep the latent in registers too
+#endif
+
 template <int L, int H, bool MULTI, int VG, int TMAX, bool GRAD>
 __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   constexpr WLayout W = make_wlayout(L, H, MULTI);
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         const float degf = (float)(e_full1 - e_in0); // in-degree of the bus (primary)
         // the bus's latent is read by six matrix-vector products per step (3 phi + 3 L nets): keep it
         // in registers when it is small enough (L*VG <= 40), else re-read it from shared memory
-        constexpr bool MREG = (L * VG <= 40);
+        constexpr bool MREG = (L * VG <= 40) && (GNS_GRAD_MREG || !GRAD);
         float mreg[MREG ? L : 1][VG];
         if constexpr (MREG) {
 #pragma unroll
@@ -343,9 +347,13 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
                 for (int g = 0; g < VG; ++g) { z2[o][g] = lrelu(z2[o][g]); A[o][g] += z2[o][g]; }
               if constexpr (GRAD) {
-                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * EG + e * G + gcol;
+                // (the opaque zero keeps the 2H row offsets from being hoisted out of the line loop into spills)
+                const int rl = a.al.rl + opaque_zero();
+                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.esp + e;
 #pragma unroll
-                for (int o = 0; o < H; ++o) { stg_stream<VG>(ap + o * EG, z[o]); stg_stream<VG>(ap + (H + o) * EG, z2[o]); }
+                for (int o = 0; o < H; ++o) { stg_grids<VG>(ap, a.al.esp, z[o]); ap += rl; }
+#pragma unroll
+                for (int o = 0; o < H; ++o) { stg_grids<VG>(ap, a.al.esp, z2[o]); ap += rl; }
               }
             }
            }
@@ -363,10 +371,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             }
           }
           if (!prim) continue;
-          float* const ab = GRAD ? act_k + (size_t)(q * 3 * H) * NG + n * G + gcol : nullptr;
+          float* const ab = GRAD ? act_k + (size_t)(q * 3 * H) * a.al.rb + gcol * a.al.nsp + n : nullptr;
           if constexpr (GRAD) {
 #pragma unroll
-            for (int o = 0; o < H; ++o) stg_stream<VG>(ab + o * NG, A[o]);
+            for (int o = 0; o < H; ++o) stg_grids<VG>(ab + o * a.al.rb, a.al.nsp, A[o]);
           }
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
           float zL[H][VG];
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             for (int g = 0; g < VG; ++g) z2[o][g] = lrelu(z2[o][g]);
           if constexpr (GRAD) {
 #pragma unroll
-            for (int o = 0; o < H; ++o) { stg_stream<VG>(ab + (H + o) * NG, zL[o]); stg_stream<VG>(ab + (2 * H + o) * NG, z2[o]); }
+            for (int o = 0; o < H; ++o) { stg_grids<VG>(ab + (H + o) * a.al.rb, a.al.nsp, zL[o]); stg_grids<VG>(ab + (2 * H + o) * a.al.rb, a.al.nsp, z2[o]); }
           }
           if (q < 2) {
             float out[VG];

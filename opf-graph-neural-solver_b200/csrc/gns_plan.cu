@@ -87,7 +87,8 @@ int backward_extra_floats(int N, int E, int G, int L, int H, int T);
 // sub-partitions hold 3,3,2,2 warps, so the heaviest groups must end up on the 2-warp ones).
 static void balance_warps(const gns_plan* plan, Geometry* g, bool backward) {
   const int nw = g->T / 32, spw = 32 / g->NGQ;
-  const float per_line = backward ? 0.3f : 0.2f;
+  float per_line = backward ? 0.3f : 0.2f;
+  if (const char* e = std::getenv(backward ? "GNS_BWD_LINE_COST" : "GNS_FWD_LINE_COST")) per_line = (float)std::atof(e);
   std::vector<float> cost(nw, 0.f);
   for (int grp = 0; grp < nw; ++grp) {
     int mx = -1;
@@ -273,7 +274,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     const size_t nst = (size_t)(4 + md.L) * row_stride(plan->Ns * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
-    const ActLayout al = make_act_layout(md.H, md.multi ? 3 : 1, row_stride(plan->Ns * fwd.G), row_stride(plan->E * fwd.G));
+    const ActLayout al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, fwd.G);
     w.act = o; o = align(o + (size_t)fwd.nbatch * md.K * (size_t)al.total * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * make_frag_layout(md.L, md.H).step * 4);   // one block per warp
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);

@@ -10,6 +10,7 @@ def flops_fwd(N, E, K, L, H, multi=True):
     return 2 * K * (E * mac_line + N * mac_bus)
 
 def run(n_bus, S, K=4, L=20, reps=5, train=False):
+    """train: False = inference forward, True = forward + backward, "fwdonly" = training forward alone"""
     torch.manual_seed(0)
     model = pkg.GNS(latent_dim=L, hidden_dim=10, K=K, gamma=0.9, multiple_phi=True).cuda()
     model.validate_topology = False
@@ -20,7 +21,9 @@ def run(n_bus, S, K=4, L=20, reps=5, train=False):
     E = l.shape[1]
     BLG = pkg.get_BLG()
     def step():
-        if train:
+        if train == "fwdonly":
+            out = model(b, l, g, *BLG)
+        elif train:
             model.zero_grad(set_to_none=True)
             out = model(b, l, g, *BLG)
             out[2].mean().backward()
@@ -35,10 +38,10 @@ def run(n_bus, S, K=4, L=20, reps=5, train=False):
         step(); ev[i + 1].record()
     torch.cuda.synchronize()
     ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))[reps // 2]
-    fl = flops_fwd(n_bus, E, K, L, 10) * (3 if train else 1)
+    fl = flops_fwd(n_bus, E, K, L, 10) * (3 if train is True else 1)
     gps = S / (ms * 1e-3)
-    info = model._last_plan.launch_info(S, K, L, 10, True, backward=train)
-    print(f"case{n_bus} S={S} K={K} L={L} {'fwd+bwd' if train else 'fwd'}: {ms:.3f} ms  {gps/1e6:.3f} M grids/s  "
+    info = model._last_plan.launch_info(S, K, L, 10, True, backward=(train is True))
+    print(f"case{n_bus} S={S} K={K} L={L} {'fwd+bwd' if train is True else ('fwd(train)' if train else 'fwd')}: {ms:.3f} ms  {gps/1e6:.3f} M grids/s  "
           f"{gps*fl/1e12:.2f} TFLOP/s algorithmic  geom={info} env VG={os.environ.get('GNS_FWD_VG')} NGQ={os.environ.get('GNS_FWD_NGQ')}", flush=True)
 
 if __name__ == "__main__":
