@@ -65,7 +65,8 @@ int gns_dims_supported(int latent_dim, int hidden_dim);
 int64_t gns_param_count(int K, int latent_dim, int hidden_dim, int multiple_phi);
 
 /* Bytes of device scratch for a batch of S grids.  need_grad != 0 adds the per-step
- * checkpoints and the gradient partial sums that gns_backward consumes. */
+ * checkpoints (state and hidden activations of every step, about 1 MB per case300
+ * grid for K=4) and the gradient partial sums that gns_backward consumes. */
 int64_t gns_workspace_bytes(const gns_plan* plan, int64_t S, int K, int latent_dim,
                             int hidden_dim, int multiple_phi, int need_grad);
 
