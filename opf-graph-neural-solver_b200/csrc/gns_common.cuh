@@ -234,6 +234,28 @@ template <int VG> __device__ __forceinline__ void stg_grids(float* p, int gstrid
 }
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }
+// LeakyReLU / accumulate over the VG grids of a thread; two grids use the packed f32x2 multiply / add of sm_100
+// (FMUL2 / FADD2: one issue slot for both grids), the max stays scalar
+template <int VG>
+__device__ __forceinline__ void lrelu_vec(float (&x)[VG]) {
+  if constexpr (VG == 2) {
+    const float2 t = __fmul2_rn(make_float2(x[0], x[1]), make_float2(kSlope, kSlope));
+    x[0] = fmaxf(x[0], t.x); x[1] = fmaxf(x[1], t.y);
+  } else {
+#pragma unroll
+    for (int g = 0; g < VG; ++g) x[g] = lrelu(x[g]);
+  }
+}
+template <int VG>
+__device__ __forceinline__ void add_vec(float (&a)[VG], const float (&b)[VG]) {
+  if constexpr (VG == 2) {
+    const float2 t = __fadd2_rn(make_float2(a[0], a[1]), make_float2(b[0], b[1]));
+    a[0] = t.x; a[1] = t.y;
+  } else {
+#pragma unroll
+    for (int g = 0; g < VG; ++g) a[g] += b[g];
+  }
+}
 __device__ __forceinline__ float lrelu_grad(float z) { return z > 0.f ? 1.f : kSlope; }   // also valid on h = lrelu(z)
 
 // sin and cos of one float, branch-free: three-constant Cody-Waite reduction by pi/2 with FMAs,
@@ -329,7 +351,8 @@ __device__ __forceinline__ void row_dot(float (&out)[VG], const float (&h)[H][VG
       t1 = fma2(make_float2(h[o + 1][0], h[o + 1][1]), make_float2(w[o + 1], w[o + 1]), t1);
     }
     if (H & 1) t0 = fma2(make_float2(h[H - 1][0], h[H - 1][1]), make_float2(w[H - 1], w[H - 1]), t0);
-    out[0] = t0.x + t1.x; out[1] = t0.y + t1.y;
+    const float2 tt = __fadd2_rn(t0, t1);
+    out[0] = tt.x; out[1] = tt.y;
   } else if constexpr (VG == 1) {
     float2 t = make_float2(0.f, 0.f);
 #pragma unroll

@@ -336,16 +336,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
                 float b[HP];
                 load_row<HP>(b, wphi + W.phi_b2);
 #pragma unroll
-                for (int o = 0; o < H; ++o)
+                for (int o = 0; o < H; ++o) {
 #pragma unroll
-                  for (int g = 0; g < VG; ++g) { z2[o][g] = b[o]; z[o][g] = lrelu(z[o][g]); }
+                  for (int g = 0; g < VG; ++g) z2[o][g] = b[o];
+                  lrelu_vec<VG>(z[o]);
+                }
               }
 #pragma unroll
               for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(z2, z[j], wphi + W.phi_w2 + j * HP);
 #pragma unroll
-              for (int o = 0; o < H; ++o)
-#pragma unroll
-                for (int g = 0; g < VG; ++g) { z2[o][g] = lrelu(z2[o][g]); A[o][g] += z2[o][g]; }
+              for (int o = 0; o < H; ++o) { lrelu_vec<VG>(z2[o]); add_vec<VG>(A[o], z2[o]); }
               if constexpr (GRAD) {
                 // (the opaque zero keeps the 2H row offsets from being hoisted out of the line loop into spills)
                 const int rl = a.al.rl + opaque_zero();
@@ -414,16 +414,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             float b[HP];
             load_row<HP>(b, wln + W.ln_b2);
 #pragma unroll
-            for (int o = 0; o < H; ++o)
+            for (int o = 0; o < H; ++o) {
 #pragma unroll
-              for (int g = 0; g < VG; ++g) { z2[o][g] = b[o]; zL[o][g] = lrelu(zL[o][g]); }
+              for (int g = 0; g < VG; ++g) z2[o][g] = b[o];
+              lrelu_vec<VG>(zL[o]);
+            }
           }
 #pragma unroll
           for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(z2, zL[j], wln + W.ln_w2 + j * HP);
 #pragma unroll
-          for (int o = 0; o < H; ++o)
-#pragma unroll
-            for (int g = 0; g < VG; ++g) z2[o][g] = lrelu(z2[o][g]);
+          for (int o = 0; o < H; ++o) lrelu_vec<VG>(z2[o]);
           if constexpr (GRAD) {
 #pragma unroll
             for (int o = 0; o < H; ++o) { stg_grids<VG>(ab + (H + o) * a.al.rb, a.al.nsp, zL[o]); stg_grids<VG>(ab + (2 * H + o) * a.al.rb, a.al.nsp, z2[o]); }
@@ -450,8 +450,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
               for (int g = 0; g < VG; ++g) dm[g] = bo;
               row_dot<H, HP, VG>(dm, z2, wln + W.ln_wo + i * HP);
               IO::ld(mi, st + (4 + i) * NG);
-#pragma unroll
-              for (int g = 0; g < VG; ++g) mi[g] += dm[g];
+              add_vec<VG>(mi, dm);
               IO::st(st + (4 + i) * NG, mi);
             }
           }
