@@ -284,6 +284,78 @@ __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
   c = ((qi + 1) & 2) ? -c0 : c0;
 }
 
+// ---- packed pairs: the two grids of a VG=2 thread as one f32x2 value (FADD2 / FMUL2 / FFMA2 of sm_100) ----
+// Same IEEE roundings per component as the scalar operators; a - b is fma(b, -1, a) (exact product).
+struct Pk2 { float2 v; };
+__device__ __forceinline__ Pk2 pk2(float a, float b) { return Pk2{make_float2(a, b)}; }
+__device__ __forceinline__ Pk2 pk2(float a) { return Pk2{make_float2(a, a)}; }
+__device__ __forceinline__ Pk2 operator+(Pk2 a, Pk2 b) { return Pk2{__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ Pk2 operator-(Pk2 a, Pk2 b) { return Pk2{__ffma2_rn(b.v, make_float2(-1.f, -1.f), a.v)}; }
+__device__ __forceinline__ Pk2 operator*(Pk2 a, Pk2 b) { return Pk2{__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ Pk2 operator*(Pk2 a, float b) { return Pk2{__fmul2_rn(a.v, make_float2(b, b))}; }
+__device__ __forceinline__ Pk2 operator-(Pk2 a) { return Pk2{make_float2(-a.v.x, -a.v.y)}; }
+__device__ __forceinline__ Pk2 vfma(Pk2 a, Pk2 b, Pk2 c) { return Pk2{__ffma2_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ Pk2 vfma(Pk2 a, float b, Pk2 c) { return Pk2{__ffma2_rn(a.v, make_float2(b, b), c.v)}; }
+__device__ __forceinline__ Pk2 vfma(Pk2 a, float b, float c) { return Pk2{__ffma2_rn(a.v, make_float2(b, b), make_float2(c, c))}; }
+__device__ __forceinline__ Pk2 vabs(Pk2 a) { return Pk2{make_float2(fabsf(a.v.x), fabsf(a.v.y))}; }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vabs(float a) { return fabsf(a); }
+
+// fast_sincos for a packed pair: the Cody-Waite reduction and both polynomials run as f32x2 operations,
+// only the rounding to the quadrant and the final selects are per component.  Bit-identical to fast_sincos.
+__device__ __forceinline__ void fast_sincos(Pk2 x, Pk2& s, Pk2& c) {
+  const Pk2 t = x * 0.63661977236758134f;
+  const Pk2 q = pk2(rintf(t.v.x), rintf(t.v.y));
+  Pk2 r = vfma(q, -1.57079637050628662e+00f, x);
+  r = vfma(q, 4.37113900018624283e-08f, r);
+  r = vfma(q, 1.71512449632429490e-15f, r);
+  const int qx = (int)q.v.x, qy = (int)q.v.y;
+  const Pk2 r2 = r * r;
+  Pk2 ps = vfma(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = vfma(ps, r2, pk2(-1.6666654611e-1f));
+  const Pk2 sr = vfma(ps * r2, r, r);
+  Pk2 pc = vfma(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = vfma(pc, r2, pk2(4.166664568298827e-2f));
+  const Pk2 cr = vfma(pc * r2, r2, vfma(r2, -0.5f, 1.0f));
+  const float sx0 = (qx & 1) ? cr.v.x : sr.v.x, cx0 = (qx & 1) ? sr.v.x : cr.v.x;
+  const float sy0 = (qy & 1) ? cr.v.y : sr.v.y, cy0 = (qy & 1) ? sr.v.y : cr.v.y;
+  s = pk2((qx & 2) ? -sx0 : sx0, (qy & 2) ? -sy0 : sy0);
+  c = pk2(((qx + 1) & 2) ? -cx0 : cx0, ((qy + 1) & 2) ? -cy0 : cy0);
+}
+
+// Per-line Kirchhoff terms of one step (ref GNS/main.py:38-41, 66-72, 87-99), for one
+// grid (T = float) or the two grids of a thread at once (T = Pk2).  Inputs: v / theta of the line's ends,
+// Y, b, 1/tau, shift of the alias lines A = f_e and B = t_e, and D, sin D, cos D of those alias lines.
+template <class T>
+struct LineTerms { T msg, pf, qf, pt, qt; };
+template <class T>
+__device__ __forceinline__ LineTerms<T> line_terms(T vf, T vt, T thf, T tht, T Yf, T bf, T itf, T shf, T Df, T sDf, T cDf,
+                                                  T Yt, T bt, T itt, T sht, T Dt, T sDt) {
+  const T a1 = ((thf - tht) - Df) - shf;
+  const T a2 = ((tht - thf) - Df) + shf;
+  const T a3 = ((tht - thf) + Dt) - sht;              // delta_ji = -delta_ij, re-read through the alias
+  T s1, c1, s2, c2, s3, c3;
+  fast_sincos(a1, s1, c1);
+  fast_sincos(a2, s2, c2);
+  fast_sincos(a3, s3, c3);
+  (void)c2;
+  const T t1 = ((vf * vt) * Yf) * itf;
+  const T vft = vf * itf;                               // v_f / tau_f
+  const T vft2 = vft * vft;
+  const T yfs = Yf * sDf;
+  LineTerms<T> o;
+  // | v_f v_t Y/tau (sin a1 + sin a2) + (v_f / tau^2) Y sin D + v_t^2 Y sin D |   (note v_f / tau^2, quirk Q5)
+  o.msg = vabs(vfma(t1, s1 + s2, vfma(vf * (itf * itf), yfs, (vt * vt) * yfs)));
+  o.pf = vfma(t1, s1, vft2 * yfs);
+  o.qf = vfma(t1 * -1.0f, c1, vft2 * vfma(Yf, cDf, bf * -0.5f));
+  const T u1 = ((vt * vf) * Yt) * itt;
+  const T sdt = sDt * -1.0f;
+  const T vt2 = vt * vt;
+  o.pt = vfma(u1, s3, (vt2 * Yt) * sdt);
+  o.qt = vfma(u1 * -1.0f, c3, vt2 * vfma(Yt, sdt, bt * -0.5f));   // yes sin, the reference's own line (quirk Q5)
+  return o;
+}
+
 // An integer zero the optimiser cannot see through.  Added to a shared-memory weight
 // pointer inside a data-dependent loop it stops loop-invariant code motion from hoisting
 // every weight row of the loop body into registers (and from there into local-memory

@@ -475,8 +475,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         float tf[VG], tt[VG], d[VG], sd[VG], cd[VG];
         IO::ld(tf, s_state + 1 * NG + (int)t_fi[j] * G + gcol);
         IO::ld(tt, s_state + 1 * NG + (int)t_ti[j] * G + gcol);
+        if constexpr (VG == 2) {
+          const Pk2 dd = pk2(tf[0], tf[1]) - pk2(tt[0], tt[1]);
+          Pk2 s2v, c2v;
+          fast_sincos(dd, s2v, c2v);
+          d[0] = dd.v.x; d[1] = dd.v.y; sd[0] = s2v.v.x; sd[1] = s2v.v.y; cd[0] = c2v.v.x; cd[1] = c2v.v.y;
+        } else {
 #pragma unroll
-        for (int g = 0; g < VG; ++g) { d[g] = tf[g] - tt[g]; fast_sincos(d[g], sd[g], cd[g]); }
+          for (int g = 0; g < VG; ++g) { d[g] = tf[g] - tt[g]; fast_sincos(d[g], sd[g], cd[g]); }
+        }
         IO::st(s_trig + 0 * NG + j * G + gcol, d);
         IO::st(s_trig + 1 * NG + j * G + gcol, sd);
         IO::st(s_trig + 2 * NG + j * G + gcol, cd);
@@ -514,27 +521,21 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         IO::ld(Dt, s_trig + 0 * NG + ta * G + gcol);
         IO::ld(sDt, s_trig + 1 * NG + ta * G + gcol);
         float pf[VG], qf[VG], pt[VG], qt[VG];
+        if constexpr (VG == 2) {   // both grids in packed f32x2 arithmetic
+          auto P = [](const float (&x)[VG]) { return pk2(x[0], x[1]); };
+          const LineTerms<Pk2> o = line_terms<Pk2>(P(vf), P(vt), P(thf), P(tht), P(Yf), P(bf), P(tauf), P(shf), P(Df), P(sDf),
+                                                   P(cDf), P(Yt), P(bt), P(taut), P(sht), P(Dt), P(sDt));
+          pj[0] += o.msg.v.x; pj[1] += o.msg.v.y;
+          pf[0] = o.pf.v.x; pf[1] = o.pf.v.y; qf[0] = o.qf.v.x; qf[1] = o.qf.v.y;
+          pt[0] = o.pt.v.x; pt[1] = o.pt.v.y; qt[0] = o.qt.v.x; qt[1] = o.qt.v.y;
+        } else {
 #pragma unroll
-        for (int g = 0; g < VG; ++g) {
-          const float dt = -Dt[g], sdt = -sDt[g];       // delta_ji = -delta_ij, re-read through the alias
-          const float a1 = thf[g] - tht[g] - Df[g] - shf[g];
-          const float a2 = tht[g] - thf[g] - Df[g] + shf[g];
-          const float a3 = tht[g] - thf[g] - dt - sht[g];
-          float s1, c1, s2, c2, s3, c3;
-          fast_sincos(a1, s1, c1);
-          fast_sincos(a2, s2, c2);
-          fast_sincos(a3, s3, c3);
-          (void)c2;
-          const float t1 = vf[g] * vt[g] * Yf[g] * tauf[g];
-          const float vft = vf[g] * tauf[g];
-          const float msg = fabsf(t1 * (s1 + s2) + (vf[g] * (tauf[g] * tauf[g])) * Yf[g] * sDf[g] +
-                                  (vt[g] * vt[g]) * Yf[g] * sDf[g]);
-          pj[g] += msg;
-          pf[g] = t1 * s1 + (vft * vft) * Yf[g] * sDf[g];
-          qf[g] = -t1 * c1 + (vft * vft) * (Yf[g] * cDf[g] - bf[g] / 2.f);
-          const float u1 = vt[g] * vf[g] * Yt[g] * taut[g];
-          pt[g] = u1 * s3 + (vt[g] * vt[g]) * Yt[g] * sdt;
-          qt[g] = -u1 * c3 + (vt[g] * vt[g]) * (Yt[g] * sdt - bt[g] / 2.f);
+          for (int g = 0; g < VG; ++g) {
+            const LineTerms<float> o = line_terms<float>(vf[g], vt[g], thf[g], tht[g], Yf[g], bf[g], tauf[g], shf[g], Df[g],
+                                                         sDf[g], cDf[g], Yt[g], bt[g], taut[g], sht[g], Dt[g], sDt[g]);
+            pj[g] += o.msg;
+            pf[g] = o.pf; qf[g] = o.qf; pt[g] = o.pt; qt[g] = o.qt;
+          }
         }
         IO::st(s_flow + 0 * EG + e * G + gcol, pf);
         IO::st(s_flow + 1 * EG + e * G + gcol, qf);
