@@ -104,6 +104,16 @@ int gns_check_topology(const gns_plan* plan, const float* lines, const float* ge
 /* Launch geometry chosen for this plan/model (for bench/roofline reporting):
  * out[0]=grids per CTA, out[1]=threads per CTA, out[2]=dynamic smem bytes,
  * out[3]=CTAs launched for S grids, out[4]=vector width (grids per thread). */
+/* Layout maps of the gradient path, for tests and tools (host only, no GPU needed).
+ *   "pack": canonical (state_dict order, all K steps) index -> packed index        [gns_param_count]
+ *   "frag": packed index inside ONE step's block -> index inside that step's fragment-order
+ *           accumulator block of gns_backward, or -1 (padding, and the W4 / b4 / W1-slice entries the
+ *           fused block's chain rule fills in)                                      [packed step size]
+ * Returns the number of entries (writes them when out != NULL and capacity suffices), -1 on error.
+ * Replaces nothing in the reference: autograd keeps its own bookkeeping (ref GNS/main.py:288). */
+int gns_layout_export(const char* name, int K, int latent_dim, int hidden_dim, int multiple_phi,
+                      int32_t* out, int capacity);
+
 int gns_launch_info(const gns_plan* plan, int64_t S, int K, int latent_dim, int hidden_dim,
                     int multiple_phi, int backward, int32_t out[8]);
 

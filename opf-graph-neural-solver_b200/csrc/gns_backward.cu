@@ -6,6 +6,7 @@
 
 #include "gns_backward.cuh"
 #include "gns_host.h"
+#include "../../include/gns_b200.h"
 
 namespace gns {
 
@@ -224,3 +225,23 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
 }
 
 }  // namespace gns
+
+extern "C" int gns_layout_export(const char* name, int K, int latent_dim, int hidden_dim, int multiple_phi,
+                                 int32_t* out, int capacity) {
+  using namespace gns;
+  if (!name || K < 1 || K > kMaxK || !gns_dims_supported(latent_dim, hidden_dim)) {
+    set_error("gns_layout_export: bad arguments"); return -1;
+  }
+  const ModelDims md{K, latent_dim, hidden_dim, multiple_phi};
+  std::vector<int32_t> v;
+  const std::string n(name);
+  if (n == "pack") v = build_pack_map(md);
+  else if (n == "frag") v = build_frag_map(md);
+  else { set_error("gns_layout_export: unknown map '" + n + "'"); return -1; }
+  if (out) {
+    if (capacity < (int)v.size()) { set_error("gns_layout_export: capacity too small"); return -1; }
+    std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
+  }
+  return (int)v.size();
+}
+

@@ -217,3 +217,49 @@ def test_device_augmenter_follows_recipe_on_cpu_device():
     assert torch.allclose(b[:, :, 4], torch.full_like(b[:, :, 4], 0.01)) and torch.allclose(b[:, :, 5], torch.full_like(b[:, :, 5], -0.01))
     b2, _, _ = pkg.data.augment_pack_device(case, 64, seed=5, device="cpu")
     assert torch.equal(b, b2)
+
+
+@pytest.mark.parametrize("L,multi", [(20, 1), (20, 0), (10, 1), (64, 1)])
+def test_gradient_layout_maps_cover_every_parameter_once(lib, L, multi):
+    """The backward kernel accumulates weight gradients in MMA-fragment order; `frag` maps the packed layout
+    onto it.  Every canonical parameter must be reachable exactly once: either through a fragment cell, or as one
+    of the entries the fused block's chain rule derives (linear4 of the phi nets and the S-slice of the L-nets'
+    linear1, ref GNS/main.py:157-171)."""
+    import ctypes as C
+    K, H = 3, 10
+    def export(name):
+        n = lib.gns_layout_export(name.encode(), K, L, H, multi, None, 0)
+        assert n > 0, pkg._lib.last_error()
+        buf = (C.c_int32 * n)()
+        assert lib.gns_layout_export(name.encode(), K, L, H, multi, buf, n) == n
+        return np.frombuffer(buf, dtype=np.int32).copy()
+    pack, frag = export("pack"), export("frag")
+    assert len(pack) == lib.gns_param_count(K, L, H, multi)
+    assert len(np.unique(pack)) == len(pack)                       # canonical -> packed is injective
+    wstep = len(frag)
+    used = frag[frag >= 0]
+    assert len(np.unique(used)) == len(used)                       # no two packed entries share a fragment cell
+    # names of the canonical parameters, in order
+    m = pkg.GNS(latent_dim=L, hidden_dim=H, K=K, multiple_phi=bool(multi))
+    names = []
+    for n, p in m.named_parameters():
+        names += [n] * p.numel()
+    assert len(names) == len(pack)
+    sizes = {n: p.shape for n, p in m.named_parameters()}
+    offs, seen = {}, {}
+    for i, n in enumerate(names):
+        offs.setdefault(n, i)
+    derived = 0
+    for i, n in enumerate(names):
+        step_local = pack[i] % wstep
+        if frag[step_local] >= 0:
+            continue
+        derived += 1
+        net, _, layer, kind = n.split(".")
+        if net.startswith("phi"):
+            assert layer == "linear4", n                           # W4 / b4 come from dM / dc
+        else:
+            assert layer == "linear1" and kind == "weight", n      # ... and so does W1[:, 4+L:]
+            col = (i - offs[n]) % sizes[n][1]
+            assert col >= 4 + L, (n, col)
+    assert derived > 0
