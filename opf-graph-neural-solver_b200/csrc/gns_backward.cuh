@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
   const uint16_t* const t_ine = s_topo + a.to.in_e;
   const uint16_t* const t_infe = s_topo + a.to.in_fe;
   const uint16_t* const t_ini = s_topo + a.to.in_ids;
+  const uint16_t* const t_inp = s_topo + a.to.in_pos;
   const uint16_t* const t_outb = s_topo + a.to.out_b;
   const uint16_t* const t_oute = s_topo + a.to.out_e;
   const uint16_t* const t_outi = s_topo + a.to.out_ids;
@@ -498,6 +499,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
         for (int i = 0; i < (AMREG ? L : 1); ++i) amr[i] = 0.f;
 
+        // line activations (h1, h2 of one phi evaluation) travel one iteration ahead of their use: the loads of
+        // iteration 0 are issued in front of the L-net's first-layer tile, those of it+1 at the top of iteration it
+        // (the iteration-major in_pos columns are read once, so there is no L1 reuse to wait for)
+        float nh[2 * H];
+        auto load_line = [&](const float* actl, int it) {
+          const float* ap = actl + (int)t_inp[(slot_on && it < deg) ? e_in0 + it : 0];
+#pragma unroll
+          for (int o = 0; o < 2 * H; ++o) nh[o] = __ldg(ap + o * RL);
+        };
         // adjoint of one phi net given adjA: line loop, dW2 / db2 / dW1f, adjP, dW1m / db1, adj m
         auto phi_backward = [&](const float* wphi, float* gphi, const float* actl) {
           float adjP[H];
@@ -511,10 +521,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             const bool live = slot_on && (it < deg);
             const float* wp = wphi + opaque_zero();
             const int e = live ? e_in0 + it : 0;                 // position in the in-list
-            const float* ap = actl + e;
             float h1[H], h2[H], d2[H][1], d1[H], feat[5];
 #pragma unroll
-            for (int o = 0; o < H; ++o) { h1[o] = __ldg(ap + o * RL); h2[o] = __ldg(ap + (H + o) * RL); }
+            for (int o = 0; o < H; ++o) { h1[o] = nh[o]; h2[o] = nh[H + o]; }   // fetched one iteration ahead
+            if (it + 1 < warp_max_deg) load_line(actl, it + 1);
             const float* lf = s_linef + (int)t_ini[e] * G + gq;
 #pragma unroll
             for (int c = 0; c < 5; ++c) feat[c] = lf[c * EG];
@@ -649,6 +659,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
           for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, d1[o][0]);
           __syncwarp();
+          const float* const actl = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * RL + (size_t)cf * a.al.esp;
+          if ((MULTI || qq == 2) && warp_max_deg > 0) load_line(actl, 0);
           // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
           tile_gemm_r<H, 4 + L + H + 2>(
               [&](int r) {
@@ -692,7 +704,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           }
           __syncwarp();
           if (MULTI || qq == 2)
-            phi_backward(wphi, gphi, act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * RL + (size_t)cf * a.al.esp);
+            phi_backward(wphi, gphi, actl);
         }
         if constexpr (AMREG) {
           if (bus_on) {

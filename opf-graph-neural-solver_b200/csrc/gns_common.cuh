@@ -128,8 +128,7 @@ __host__ __device__ constexpr int frag_index(int r, int c) {
 // kernel neither recomputes the forward nor needs the pre-activations (h > 0 <=> z > 0):
 //   per bus and pair q:   A (aggregate, H), h1 and h2 of the L-net (H each)    rows [q][3H][NGs]
 //   per line and phi net: h1 and h2 of the phi net (H each)                    rows [p][2H][EGs]
-// in the forward kernel's grid-interleaved layout; a line is addressed by its position in the
-// plan's in-list (each position is walked by exactly one slot).  172 floats per bus and step on
+// a line is addressed through the plan's in_pos table (iteration-major over the slots that walk it).  172 floats per bus and step on
 // case300: 867 KB per grid for K=4, streamed once out and once in (~1.3 TB/s at 0.75 M grids/s).
 // ---------------------------------------------------------------------------------
 // Rows are GRID-MAJOR, [row][grid][item] with every (row, grid) segment padded to a 128-byte multiple: the
@@ -157,6 +156,8 @@ struct TopoOffsets {      // offsets in uint16 units inside the index block
   int fa, ta;             // [E] alias line ids: external from / to bus number re-read as a line id
   int in_b, in_e, in_fe;  // [Ns] in-line range walked by this slot; end of the bus's full range (primary)
   int in_ids;             // [E] line ids grouped by receiving bus (ascending line id inside a bus)
+  int in_pos;             // [E] activation-checkpoint column of in-list position e: positions walked in the same iteration by
+                          //     consecutive slots are consecutive, so the line records of a warp are written / read coalesced
   int out_b, out_e;       // [Ns] out-line range (primary slots only, else empty)
   int out_ids;            // [E]
   int gen_b, gen_e;       // [Ns] generator range (primary slots only)
@@ -179,6 +180,7 @@ __host__ __device__ inline TopoOffsets make_topo_offsets(int N, int Ns, int E, i
   t.in_e = o; o += Ns;
   t.in_fe = o; o += Ns;
   t.in_ids = o; o += E;
+  t.in_pos = o; o += E;
   t.out_b = o; o += Ns;
   t.out_e = o; o += Ns;
   t.out_ids = o; o += E;

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const uint16_t* const t_ine = s_topo + a.to.in_e;
   const uint16_t* const t_infe = s_topo + a.to.in_fe;
   const uint16_t* const t_ini = s_topo + a.to.in_ids;
+  const uint16_t* const t_inp = s_topo + a.to.in_pos;
   const uint16_t* const t_outb = s_topo + a.to.out_b;
   const uint16_t* const t_oute = s_topo + a.to.out_e;
   const uint16_t* const t_outi = s_topo + a.to.out_ids;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
               if constexpr (GRAD) {
                 // (the opaque zero keeps the 2H row offsets from being hoisted out of the line loop into spills)
                 const int rl = a.al.rl + opaque_zero();
-                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.esp + e;
+                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.esp + (int)t_inp[e];
 #pragma unroll
                 for (int o = 0; o < H; ++o) { stg_grids<VG>(ap, a.al.esp, z[o]); ap += rl; }
 #pragma unroll

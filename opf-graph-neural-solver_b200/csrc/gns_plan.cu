@@ -392,6 +392,13 @@ extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* 
       blk[p->to.gen_e + ps] = (uint16_t)og;
       blk[p->to.rank_of + b] = (uint16_t)ps;
     }
+    {   // in_pos: iteration-major numbering of the in-list positions
+      int maxw = 0, next = 0;
+      for (int s = 0; s < Ns; ++s) maxw = std::max(maxw, p->slot_in_end[s] - p->slot_in_begin[s]);
+      for (int it = 0; it < maxw; ++it)
+        for (int s = 0; s < Ns; ++s)
+          if (p->slot_in_end[s] - p->slot_in_begin[s] > it) blk[p->to.in_pos + p->slot_in_begin[s] + it] = (uint16_t)next++;
+    }
     for (int s = 0; s < Ns; ++s) {
       blk[p->to.in_b + s] = (uint16_t)p->slot_in_begin[s];
       blk[p->to.in_e + s] = (uint16_t)p->slot_in_end[s];
