@@ -111,15 +111,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& sma
   small = __float_as_uint(x - __uint_as_float(big));
 }
 
-__device__ __forceinline__ void red_add_v4(float* p, const float (&d)[4]) {   // fire-and-forget: no load, no scoreboard wait
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d[0]), "f"(d[1]), "f"(d[2]), "f"(d[3]) : "memory");
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {   // fire-and-forget: no load, no scoreboard wait
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
 // gfrag: this call's block of the warp-private accumulator (FragLayout); only this warp ever adds to it,
 // in program order, so the reductions are deterministic.
 template <int C, int R, class RowFn>
 __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
-  static_assert(C <= 16, "hidden side must fit one m16 tile");
+  static_assert(C <= 11, "hidden columns 11..15 of the m16 tile are not stored");
   const int lane = threadIdx.x & 31, gi = lane >> 2, t = lane & 3;
   // A fragments of the four MMAs: MMA m covers items a(t, m) = 16 (m / 2) + 4 t + 2 (m % 2) and a + 1
   uint32_t ab[4][4], as[4][4];            // [mma][a0..a3], big and small parts
@@ -170,7 +170,8 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
 #pragma unroll
       for (int c = 1; c < GNS_MMA_CHAINS; ++c) d[j] += di[c][j];
     }
-    red_add_v4(gfrag + nt * 128 + lane * 4, d);
+    red_add_v2(gfrag + nt * kFragTile + lane * 2, d[0], d[1]);                               // hidden columns 0..7
+    if (C > 8 && lane < 4 * (C - 8)) red_add_v2(gfrag + nt * kFragTile + 64 + lane * 2, d[2], d[3]);   // columns 8..C-1
   }
 }
 

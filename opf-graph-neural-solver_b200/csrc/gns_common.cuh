@@ -95,31 +95,34 @@ __host__ __device__ constexpr WLayout make_wlayout(int L, int H, bool multi) {
 
 // ---------------------------------------------------------------------------------
 // Gradient accumulators of the backward kernel, in MMA-fragment order.  Every weight-gradient GEMM
-// call owns a block of NT x 128 floats ([8-row tile][lane][4 accumulator cells]) inside its warp's
-// private accumulator, so a lane adds its four cells with one 128-bit reduction and no index
-// arithmetic; build_frag_map() (host) inverts the order once per model shape.
+// call owns a block of NT x kFragTile floats inside its warp's private accumulator, so a lane adds its
+// cells with one or two 64-bit reductions and no index arithmetic; build_frag_map() (host) inverts the order once per model shape.
 // Per pair q: phi per-line W2/b2 (11 wide rows), phi per-line W1f (5), phi W1m/b1 (L+1),
 // L-net output layer (m-net: L rows x (H+1) columns; scalar nets: H+1 values, stored directly),
 // L-net second layer (H+1), L-net first layer + fused block + bias (4+L+H+2).
 // ---------------------------------------------------------------------------------
 struct FragLayout { int w2l, w1f, w1m, out, w2, w1, net, step; };
+// One 8-row tile owns kFragTile floats: [lane][2] cells of hidden columns 0..7 (64 floats), then [lane][2] cells of
+// hidden columns 8..10 for the 12 lanes that hold them (24 floats).  Columns 11..15 of the m16 tile are padding
+// and are never stored, which keeps the accumulators of 1,480 warps at 100 MB (< L2) instead of 145 MB.
+constexpr int kFragTile = 64 + 24;
 __host__ __device__ constexpr int frag_tiles(int rows) { return (rows + 7) / 8; }
 __host__ __device__ constexpr FragLayout make_frag_layout(int L, int H) {
   FragLayout f{};
   int o = 0;
-  f.w2l = o; o += 128 * frag_tiles(H + 1);
-  f.w1f = o; o += 128 * frag_tiles(5);
-  f.w1m = o; o += 128 * frag_tiles(L + 1);
-  f.out = o; o += 128 * frag_tiles(L);
-  f.w2 = o; o += 128 * frag_tiles(H + 1);
-  f.w1 = o; o += 128 * frag_tiles(4 + L + H + 2);
+  f.w2l = o; o += kFragTile * frag_tiles(H + 1);
+  f.w1f = o; o += kFragTile * frag_tiles(5);
+  f.w1m = o; o += kFragTile * frag_tiles(L + 1);
+  f.out = o; o += kFragTile * frag_tiles(L);
+  f.w2 = o; o += kFragTile * frag_tiles(H + 1);
+  f.w1 = o; o += kFragTile * frag_tiles(4 + L + H + 2);
   f.net = o;
-  f.step = 3 * o;
+  f.step = (3 * o + 31) & ~31;
   return f;
 }
-// position of cell (wide row r, hidden column c) inside a call's block
+// position of cell (wide row r, hidden column c <= 10) inside a call's block
 __host__ __device__ constexpr int frag_index(int r, int c) {
-  return (r / 8) * 128 + ((c % 8) * 4 + (r % 8) / 2) * 4 + (r % 2) + 2 * (c / 8);
+  return (r / 8) * kFragTile + (c < 8 ? 0 : 64) + ((c % 8) * 4 + (r % 8) / 2) * 2 + (r % 2);
 }
 
 // ---------------------------------------------------------------------------------
