@@ -117,7 +117,8 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {   // fi
 
 // gfrag: this call's block of the warp-private accumulator (FragLayout); only this warp ever adds to it,
 // in program order, so the reductions are deterministic.
-template <int C, int R, class RowFn>
+// CG: the wide rows live in global memory that this kernel updates with reductions: read them from L2 (ld.global.cg)
+template <int C, int R, bool CG, class RowFn>
 __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
   static_assert(C <= 11, "hidden columns 11..15 of the m16 tile are not stored");
   const int lane = threadIdx.x & 31, gi = lane >> 2, t = lane & 3;
@@ -137,14 +138,31 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
   }
   constexpr int NT = (R + 7) / 8;
   constexpr int UNR = NT <= 5 ? NT : 1;   // long tiles (latent_dim 64) stay rolled: unrolling them only buys spills
-#pragma unroll UNR
-  for (int nt = 0; nt < NT; ++nt) {
+  // B fragments of tile nt: wide row nt*8+gi, items 4t..4t+3 and 16+4t..16+4t+3 (zeros past the last row)
+  auto load_b = [&](int nt, float4& lo, float4& hi) {
     const int row = nt * 8 + gi;
     const bool rv = (nt * 8 + 8 <= R) || (row < R);
     const float* rp = rowfn(rv ? row : 0) + 4 * t;
-    float4 blo = *reinterpret_cast<const float4*>(rp);
-    float4 bhi = *reinterpret_cast<const float4*>(rp + 16);
-    if (!rv) { blo = make_float4(0.f, 0.f, 0.f, 0.f); bhi = blo; }
+    if constexpr (CG) {
+      lo = __ldcg(reinterpret_cast<const float4*>(rp));
+      hi = __ldcg(reinterpret_cast<const float4*>(rp + 16));
+    } else {
+      lo = *reinterpret_cast<const float4*>(rp);
+      hi = *reinterpret_cast<const float4*>(rp + 16);
+    }
+    if (!rv) { lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = lo; }
+  };
+  float4 nlo, nhi;                        // rolled loops (long tiles, rows possibly in global memory): one tile ahead
+  if constexpr (UNR == 1) load_b(0, nlo, nhi);
+#pragma unroll UNR
+  for (int nt = 0; nt < NT; ++nt) {
+    float4 blo, bhi;
+    if constexpr (UNR == 1) {
+      blo = nlo; bhi = nhi;
+      if (nt + 1 < NT) load_b(nt + 1, nlo, nhi);
+    } else {
+      load_b(nt, blo, bhi);
+    }
     const float bv[4][2] = {{blo.x, blo.y}, {blo.z, blo.w}, {bhi.x, bhi.y}, {bhi.z, bhi.w}};
     uint32_t bb[4][2], bs[4][2];
 #pragma unroll
@@ -177,9 +195,9 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
 
 // one weight-gradient GEMM call: rows r < R (wide side) x C hidden columns over the warp's 32 items, added
 // into the call's accumulator block
-template <int C, int R, class RowFn>
+template <int C, int R, bool CG = false, class RowFn>
 __device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
-  tile_gemm_mma<C, R>(rowfn, hidblk, gfrag);
+  tile_gemm_mma<C, R, CG>(rowfn, hidblk, gfrag);
 }
 
 // Large latent dimensions (L > 32): state m and its adjoint (2 x L x Ns floats, 183 KB for L=64 on
@@ -346,7 +364,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         if (k >= 1) {
           const float* ck = ck_base + (size_t)(k - 1) * ck_stride + (size_t)n * a.Gf;
           for (int i = 0; i < 4; ++i) s_state[i * NG + nb] = ck[(size_t)i * a.NGs_f];
-          for (int i = 0; i < L; ++i) m_rows[i * NG + nb] = ck[(size_t)(4 + i) * a.NGs_f];
+          if (!(MG && a.Gf == 1)) {   // (large latents with one grid per forward column read m in place, see rows_m)
+            for (int i = 0; i < L; ++i) m_rows[i * NG + nb] = ck[(size_t)(4 + i) * a.NGs_f];
+          }
         } else {   // state before step 0 (ref GNS/main.py:141-152)
           float vv = 0.f, pg = 0.f, qg = 0.f;
           for (int j = j0; j < j1; ++j) {
@@ -485,7 +505,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         float* adjm = am_rows + nb;
         float adj4[4] = {0.f, 0.f, 0.f, 0.f};
         const float* rows_state = s_state + 32 * grp;          // [f][item] rows of this warp's 32 items
-        const float* rows_m = m_rows + 32 * grp;
+        // Large latents: with one grid per forward column the checkpoint's m rows already are [feature][item], so the
+        // tiles read them in place (no copy into the scratch); step 0 reads the zeroed scratch rows.
+        const bool m_in_ckpt = MG && a.Gf == 1 && k >= 1;
+        const float* rows_m = m_in_ckpt ? ck_base + (size_t)(k - 1) * ck_stride + (size_t)4 * a.NGs_f + 32 * grp : m_rows + 32 * grp;
+        const int MS = m_in_ckpt ? a.NGs_f : NG;               // row stride of rows_m
         const float* rows_am = am_rows + 32 * grp;
         // this grid's column of the activations the forward kernel kept for step k (no recompute here)
         const float* const act_k = a.act + ((size_t)bf * K + k) * (size_t)a.al.total;
@@ -568,7 +592,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, adjP[o]);
           __syncwarp();
           // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
-          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * NG : tile + T_ONES; }, tile + T_HIDA, gphi + FL.w1m);
+          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * MS : tile + T_ONES; }, tile + T_HIDA, gphi + FL.w1m);
           {
             float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
             if constexpr (AMREG) {
@@ -583,7 +607,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
               for (int i = 0; i < L; ++i) {
                 float t[1] = {0.f};
                 row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
-                if (bus_on) adjm[i * NG] += t[0];
+                if (bus_on) atomicAdd(adjm + i * NG, t[0]);   // global scratch (L > 32): fire-and-forget reduction, no load
               }
             }
           }
@@ -628,7 +652,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           } else {
 #pragma unroll 2
             for (int i = 0; i < L; ++i) {
-              float gm[1] = {bus_on ? adjm[i * NG] : 0.f};
+              float gm[1] = {bus_on ? (MG ? __ldcg(adjm + i * NG) : adjm[i * NG]) : 0.f};   // (the scratch is updated by reductions in L2)
               row_axpy<H, HP, 1>(dh2, gm, wln + W.ln_wo + i * HP);
             }
 #pragma unroll
@@ -636,7 +660,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             stage_hid(T_HIDA, H, 1.f);
             __syncwarp();
             // dWout[i][j] += adjm'[i] h2[j];  dbout[i] += adjm'[i]    (rows = adj m' rows in place)
-            tile_gemm_r<H + 1, L>([&](int r) { return rows_am + r * NG; }, tile + T_HIDA, gln + FL.out);
+            tile_gemm_r<H + 1, L, MG>([&](int r) { return rows_am + r * NG; }, tile + T_HIDA, gln + FL.out);
           }
           __syncwarp();
           // ---- second layer ----
@@ -666,7 +690,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           tile_gemm_r<H, 4 + L + H + 2>(
               [&](int r) {
                 return r < 4 ? rows_state + r * NG
-                       : r < 4 + L ? rows_m + (r - 4) * NG
+                       : r < 4 + L ? rows_m + (r - 4) * MS
                                  : (r < 4 + L + H + 1 ? tile + T_S + (r - 4 - L) * kTS : tile + T_ONES);
               },
               tile + T_HIDA, gln + FL.w1);
@@ -690,7 +714,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             for (int i = 0; i < L; ++i) {
               float t[1] = {0.f};
               row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
-              if (bus_on) adjm[i * NG] += t[0];
+              if (bus_on) atomicAdd(adjm + i * NG, t[0]);
             }
           }
           if (MULTI) {
