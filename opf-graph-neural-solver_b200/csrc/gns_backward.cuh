@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             // dWout[j] += g h2[j];  dbout += g      (rows = [h2 (H), ones], one column g)
             tile_gemm_r<1, H + 1>([&](int r) { return tile + (r < H ? T_WIDE + r * kTS : T_ONES); }, tile + T_HIDA, gln + FL.out);
           } else {
-#pragma unroll 2
+            constexpr int UG = MG ? 8 : 2;      // adj m' in the global scratch: more L2 loads in flight
+#pragma unroll UG
             for (int i = 0; i < L; ++i) {
               float gm[1] = {bus_on ? (MG ? __ldcg(adjm + i * NG) : adjm[i * NG]) : 0.f};   // (the scratch is updated by reductions in L2)
               row_axpy<H, HP, 1>(dh2, gm, wln + W.ln_wo + i * HP);
