@@ -363,10 +363,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       if (bus_on) {
         if (k >= 1) {
           const float* ck = ck_base + (size_t)(k - 1) * ck_stride + (size_t)n * a.Gf;
-          for (int i = 0; i < 4; ++i) s_state[i * NG + nb] = ck[(size_t)i * a.NGs_f];
-          if (!(MG && a.Gf == 1)) {   // (large latents with one grid per forward column read m in place, see rows_m)
+          // asynchronous copies straight into shared memory; they are waited for in front of the barrier of the
+          // lambda-coupling reduction below, under the trig of the alias lines
+          for (int i = 0; i < 4; ++i) cp_async4(s_state + i * NG + nb, ck + (size_t)i * a.NGs_f);
+          if constexpr (!MG) {
+            for (int i = 0; i < L; ++i) cp_async4(m_rows + i * NG + nb, ck + (size_t)(4 + i) * a.NGs_f);
+          } else if (a.Gf != 1) {     // (large latents with one grid per forward column read m in place, see rows_m)
             for (int i = 0; i < L; ++i) m_rows[i * NG + nb] = ck[(size_t)(4 + i) * a.NGs_f];
           }
+          cp_async_commit();
         } else {   // state before step 0 (ref GNS/main.py:141-152)
           float vv = 0.f, pg = 0.f, qg = 0.f;
           for (int j = j0; j < j1; ++j) {
@@ -413,7 +418,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         fast_sincos(d, sd, cd);
         s_trig[0 * NG + jb] = d; s_trig[1 * NG + jb] = sd; s_trig[2 * NG + jb] = cd;
       }
-      block_sum_per_grid<1>(part, s_red, NGQ, red_parity);      // its barrier also publishes s_w, s_state, s_trig, gdP
+      cp_async_wait_all();                                      // this thread's state_k rows have landed
+      block_sum_per_grid<1>(part, s_red, NGQ, red_parity);      // its barrier also publishes s_state, s_trig, gdP
       const float adj_pg = part[0] / (lo_branch ? 2.f * (sPset - sPmin) : 2.f * (sPmax - sPset));
 
       // ---------------- physics adjoint (b): per-line partials ----------------

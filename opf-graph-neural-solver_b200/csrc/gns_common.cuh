@@ -471,6 +471,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 4-byte asynchronous global -> shared copies (LDGSTS): no register staging, no scoreboard wait at the issue
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // 16-byte aligned window [begin, begin+bytes) covering elements [first, first+count) of a float array
 struct BulkWindow { long long begin; uint32_t bytes; int shift; };   // shift = floats between window start and `first`
 __device__ __forceinline__ BulkWindow bulk_window(long long first, int count) {
