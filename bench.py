@@ -207,7 +207,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU for the default arm (there is no CPU fallback path)")
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 meanwhile (NCCL prints its version
+    # banner there) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
+    numa_bound = pkg.parallel.bind_to_gpu_numa_node(local) if world > 1 else False
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -311,7 +317,7 @@ def run_ours(args):
         pass
     info = plan.launch_info(S, K, L, 10, True)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--case", str(case),
                                 "--K", str(K), "--latent", str(L), "--cpu-sample", str(args.cpu_sample or 256)],
@@ -347,7 +353,9 @@ def run_ours(args):
         "gpu_launches": 3 * args.steps + 7 * args.steps + max(2, args.steps // 2) * 3 * ((S + 8191) // 8192),
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    line["config"]["numa_bound"] = numa_bound
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

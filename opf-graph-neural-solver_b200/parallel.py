@@ -3,8 +3,35 @@ ref GNS/main.py:279-283); training adds exactly one all-reduce of the flat gradi
 the reference's batch loss is mean(losses) (ref GNS/main.py:284)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin this process to the CPUs NVML reports as local to the GPU (one process per GPU): pinned host
+    buffers are then allocated on the GPU's NUMA node and host<->device copies do not cross sockets.
+    Returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
 
 
 def shard_range(n_items: int, rank: int, world: int):
