@@ -250,3 +250,18 @@ def test_shared_accumulator_mode_matches_within_tolerance(lib, monkeypatch):
     worst = max(float((got[n] - got2[n]).abs().max()) for n in got)
     gmax = max(float(w.abs().max()) for w in want.values())
     assert worst <= 1e-5 * gmax, f"shared vs per-warp accumulators differ by {worst:.3e} (max|g| {gmax:.3e})"
+
+
+@pytest.mark.parametrize("K", [1, 2])
+def test_short_recurrences(lib, K):
+    """K = 1 has no checkpointed state at all (the only step starts from the initial state), K = 2 one."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=K, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(30, 21, seed=4)
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    (_, _, otot, _), want = orc.gns_loss_and_grads(params, buses.double(), lines.double(), gens.double(), K=K,
+                                                   latent_dim=20, gamma=0.9, multiple_phi=True)
+    out = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    out[2].mean().backward()
+    assert_loss_close(out[2], otot, f"K={K} total")
+    assert_grads_close(_grads(model), want, f"K={K}")
