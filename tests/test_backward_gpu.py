@@ -265,3 +265,20 @@ def test_short_recurrences(lib, K):
     out[2].mean().backward()
     assert_loss_close(out[2], otot, f"K={K} total")
     assert_grads_close(_grads(model), want, f"K={K}")
+
+
+def test_odd_batch_on_the_two_grids_per_thread_forward(lib):
+    """S = 299 is large enough for the VG=2 forward (two grids per thread) and odd: the last CTA-batch holds one
+    real grid and one replicated tail grid, whose activations are written but must not reach the gradient."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(30, 299, seed=6)
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    (_, _, otot, _), want = orc.gns_loss_and_grads(params, buses.double(), lines.double(), gens.double(), K=4,
+                                                   latent_dim=20, gamma=0.9, multiple_phi=True)
+    out = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    info = model._last_plan.launch_info(299, 4, 20, 10, True)
+    assert info["vector_width"] == 2, info
+    out[2].mean().backward()
+    assert_loss_close(out[2], otot, "total")
+    assert_grads_close(_grads(model), want, "odd batch")
