@@ -219,7 +219,7 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = K; a.NGQ = gf.NGQ; a.G = gf.G; a.nbatch = gf.nbatch;
   a.NGs = row_stride(plan->Ns * gf.G); a.EGs = row_stride(plan->E * gf.G);
   a.need_grad = need_grad ? 1 : 0;
-  a.al = make_act_layout(H, multi ? 3 : 1, plan->Ns, plan->E, gf.G);
+  a.al = make_act_layout(H, multi ? 3 : 1, plan->Ns, plan->E, gf.G, need_grad ? act_grid_major(gb) : true);
   a.use_tma = (gf.sm.stage_l != 0 && ((uintptr_t)buses % 16 == 0) && ((uintptr_t)lines % 16 == 0) &&
                ((uintptr_t)gens % 16 == 0)) ? 1 : 0;
   std::memcpy(a.grp_of_warp, gf.grp_of_warp, 32);

@@ -200,7 +200,7 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K; a.NGQ = gb.NGQ; a.G = gb.G; a.nbatch = gb.nbatch;
   a.NGs = bwd_bus_stride(plan->Ns * gb.G); a.EGs = row_stride(plan->E * gb.G);
   a.Gf = gf.G; a.NGs_f = row_stride(plan->Ns * gf.G); a.EGs_f = row_stride(plan->E * gf.G);
-  a.al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, gf.G);
+  a.al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, gf.G, act_grid_major(gb));
   std::memcpy(a.grp_of_warp, gb.grp_of_warp, 32);
   a.sm = gb.sm;
   a.bs = make_bwd_smem(plan->Ns, plan->E, gb.G, md.L, md.H, md.L, nwarps, md.L > 32);

@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         // this grid's column of the activations the forward kernel kept for step k (no recompute here)
         const float* const act_k = a.act + ((size_t)bf * K + k) * (size_t)a.al.total;
         const size_t RB = (size_t)a.al.rb, RL = (size_t)a.al.rl;
+        const int AIS = a.al.is, ALS = a.al.ls;     // item strides of the two activation layouts (locals: read once per step)
         float adjA[H];
 #pragma unroll
         for (int o = 0; o < H; ++o) adjA[o] = 0.f;
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         // (the iteration-major in_pos columns are read once, so there is no L1 reuse to wait for)
         float nh[2 * H];
         auto load_line = [&](const float* actl, int it) {
-          const float* ap = actl + (int)t_inp[(slot_on && it < deg) ? e_in0 + it : 0];
+          const float* ap = actl + (int)t_inp[(slot_on && it < deg) ? e_in0 + it : 0] * ALS;
 #pragma unroll
           for (int o = 0; o < 2 * H; ++o) nh[o] = __ldg(ap + o * RL);
         };
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           // ---- activations of this bus and pair kept by the forward kernel: A, h1, h2 of the L-net ----
           float h1L[H], h2L[H];
           {
-            const float* ab = act_k + (size_t)(q * 3 * H) * RB + (size_t)cf * a.al.nsp + n;
+            const float* ab = act_k + (size_t)(q * 3 * H) * RB + (size_t)cf * a.al.gs + (size_t)n * AIS;
             float Aq[H];
 #pragma unroll
             for (int o = 0; o < H; ++o) { Aq[o] = __ldg(ab + o * RB); h1L[o] = __ldg(ab + (H + o) * RB); h2L[o] = __ldg(ab + (2 * H + o) * RB); }
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
           for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, d1[o][0]);
           __syncwarp();
-          const float* const actl = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * RL + (size_t)cf * a.al.esp;
+          const float* const actl = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * RL + (size_t)cf * a.al.gl;
           if ((MULTI || qq == 2) && warp_max_deg > 0) load_line(actl, 0);
           // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
           tile_gemm_r<H, 4 + L + H + 2>(

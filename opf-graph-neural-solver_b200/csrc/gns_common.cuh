@@ -134,14 +134,24 @@ __host__ __device__ constexpr int frag_index(int r, int c) {
 // a line is addressed through the plan's in_pos table (iteration-major over the slots that walk it).  172 floats per bus and step on
 // case300: 867 KB per grid for K=4, streamed once out and once in (~1.3 TB/s at 0.75 M grids/s).
 // ---------------------------------------------------------------------------------
-// Rows are GRID-MAJOR, [row][grid][item] with every (row, grid) segment padded to a 128-byte multiple: the
-// backward kernel works on one grid per CTA, so its lanes read consecutive floats (every fetched sector
-// fully used); the forward kernel pays one 32-bit store per grid instead of one vector store.
-struct ActLayout { int nsp, esp, rb, rl, line_off, total; };
-__host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, int E, int G) {
+// Two row layouts, chosen by the backward geometry (the reader):
+//   grid-major  [row][grid][item]  when the backward kernel works on ONE grid per CTA (large grids): its lanes are
+//               consecutive items of one grid and read consecutive floats; every (row, grid) segment is padded to
+//               a 128-byte multiple.  The forward kernel pays one 32-bit store per grid instead of a vector store.
+//   interleaved [row][item][grid]  when several grids share a CTA (small grids): the lanes of both kernels are
+//               (item, grid) pairs with the grid index fastest, exactly this order.
+// Address of (row, item, grid): row * rb + item * is + grid * gs   (bus block; rl / ls / gl for the line block).
+struct ActLayout { int rb, is, gs, rl, ls, gl, line_off, total; };
+__host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, int E, int G, bool grid_major) {
   ActLayout a{};
-  a.nsp = (Ns + 31) & ~31; a.esp = (E + 31) & ~31;     // items per (row, grid) segment
-  a.rb = G * a.nsp; a.rl = G * a.esp;                    // row strides of the bus / line blocks
+  if (grid_major) {
+    const int nsp = (Ns + 31) & ~31, esp = (E + 31) & ~31;
+    a.rb = G * nsp; a.is = 1; a.gs = nsp;
+    a.rl = G * esp; a.ls = 1; a.gl = esp;
+  } else {
+    a.rb = pad4(Ns * G); a.is = G; a.gs = 1;
+    a.rl = pad4(E * G); a.ls = G; a.gl = 1;
+  }
   a.line_off = 3 * 3 * H * a.rb;
   a.total = a.line_off + nphi * 2 * H * a.rl;
   return a;
@@ -236,6 +246,16 @@ template <> __device__ __forceinline__ void stg_stream<4>(float* p, const float 
 template <int VG> __device__ __forceinline__ void stg_grids(float* p, int gstride, const float (&x)[VG]) {
 #pragma unroll
   for (int g = 0; g < VG; ++g) __stcs(p + g * gstride, x[g]);
+}
+// N rows of VG grids each, `rstride` floats apart.  INTER: the thread's grids are adjacent in memory (interleaved
+// activation layout): one vector store per row; else one 32-bit store per grid, `gstride` floats apart.
+template <int N, int VG, bool INTER> __device__ __forceinline__ void stg_rows(float* p, int rstride, int gstride, const float (&x)[N][VG]) {
+#pragma unroll
+  for (int o = 0; o < N; ++o) {     // (pointer bumped row by row: N independent row offsets would be hoisted into spills)
+    if constexpr (INTER) stg_stream<VG>(p, x[o]);
+    else stg_grids<VG>(p, gstride, x[o]);
+    p += rstride;
+  }
 }
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }

@@ -18,8 +18,11 @@ namespace gns {
 #define GNS_GRAD_MREG 1   // training variant: keep the latent in registers too
 #endif
 
-template <int L, int H, bool MULTI, int VG, int TMAX, bool GRAD>
+// GRADV: 0 = inference, 1 = training with grid-major activation rows, 2 = training with interleaved rows (ActLayout)
+template <int L, int H, bool MULTI, int VG, int TMAX, int GRADV>
 __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
+  constexpr bool GRAD = GRADV != 0;
+  constexpr bool INTER = GRADV == 2;
   constexpr WLayout W = make_wlayout(L, H, MULTI);
   constexpr int HP = pad4(H);
   constexpr int PO = MULTI ? L : 1;
@@ -350,11 +353,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
               if constexpr (GRAD) {
                 // (the opaque zero keeps the 2H row offsets from being hoisted out of the line loop into spills)
                 const int rl = a.al.rl + opaque_zero();
-                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.esp + (int)t_inp[e];
-#pragma unroll
-                for (int o = 0; o < H; ++o) { stg_grids<VG>(ap, a.al.esp, z[o]); ap += rl; }
-#pragma unroll
-                for (int o = 0; o < H; ++o) { stg_grids<VG>(ap, a.al.esp, z2[o]); ap += rl; }
+                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.gl + (int)t_inp[e] * a.al.ls;
+                stg_rows<H, VG, INTER>(ap, rl, a.al.gl, z);
+                stg_rows<H, VG, INTER>(ap + H * rl, rl, a.al.gl, z2);
               }
             }
            }
@@ -372,10 +373,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             }
           }
           if (!prim) continue;
-          float* const ab = GRAD ? act_k + (size_t)(q * 3 * H) * a.al.rb + gcol * a.al.nsp + n : nullptr;
+          float* const ab = GRAD ? act_k + (size_t)(q * 3 * H) * a.al.rb + gcol * a.al.gs + n * a.al.is : nullptr;
           if constexpr (GRAD) {
-#pragma unroll
-            for (int o = 0; o < H; ++o) stg_grids<VG>(ab + o * a.al.rb, a.al.nsp, A[o]);
+            stg_rows<H, VG, INTER>(ab, a.al.rb, a.al.gs, A);
           }
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
           float zL[H][VG];
@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
           for (int o = 0; o < H; ++o) lrelu_vec<VG>(z2[o]);
           if constexpr (GRAD) {
-#pragma unroll
-            for (int o = 0; o < H; ++o) { stg_grids<VG>(ab + (H + o) * a.al.rb, a.al.nsp, zL[o]); stg_grids<VG>(ab + (2 * H + o) * a.al.rb, a.al.nsp, z2[o]); }
+            stg_rows<H, VG, INTER>(ab + H * a.al.rb, a.al.rb, a.al.gs, zL);
+            stg_rows<H, VG, INTER>(ab + 2 * H * a.al.rb, a.al.rb, a.al.gs, z2);
           }
           if (q < 2) {
             float out[VG];

@@ -62,6 +62,9 @@ struct Workspace {
 };
 
 bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, bool backward, Geometry* out);
+// activation checkpoints: grid-major rows iff the backward kernel works on one grid per CTA (see ActLayout);
+// GNS_ACT_LAYOUT=grid / interleaved overrides (A/B measurements)
+bool act_grid_major(const Geometry& bwd);
 Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S, bool need_grad,
                          const Geometry& fwd, const Geometry& bwd);
 

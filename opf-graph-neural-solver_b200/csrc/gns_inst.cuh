@@ -7,9 +7,9 @@
 
 namespace gns {
 
-template <int L, int H, bool MULTI, int VG, int TMAX, bool GRAD>
+template <int L, int H, bool MULTI, int VG, int TMAX, int GRADV>
 static cudaError_t launch_forward_g(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
-  auto kern = gns_forward_kernel<L, H, MULTI, VG, TMAX, GRAD>;
+  auto kern = gns_forward_kernel<L, H, MULTI, VG, TMAX, GRADV>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -21,11 +21,12 @@ static cudaError_t launch_forward_g(const FwdArgs& a, const Geometry& g, cudaStr
   return cudaGetLastError();
 }
 
-// the training variant (GRAD) also writes the state and activation checkpoints
+// the training variants also write the state and activation checkpoints (grid-major or interleaved rows)
 template <int L, int H, bool MULTI, int VG, int TMAX>
 static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
-  return a.need_grad ? launch_forward_g<L, H, MULTI, VG, TMAX, true>(a, g, st)
-                     : launch_forward_g<L, H, MULTI, VG, TMAX, false>(a, g, st);
+  if (!a.need_grad) return launch_forward_g<L, H, MULTI, VG, TMAX, 0>(a, g, st);
+  return a.al.gs == 1 ? launch_forward_g<L, H, MULTI, VG, TMAX, 2>(a, g, st)
+                      : launch_forward_g<L, H, MULTI, VG, TMAX, 1>(a, g, st);
 }
 
 template <int L, int H>

@@ -192,6 +192,14 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
   return true;
 }
 
+bool act_grid_major(const Geometry& bwd) {
+  if (const char* e = std::getenv("GNS_ACT_LAYOUT")) {
+    if (e[0] == 'g') return true;
+    if (e[0] == 'i') return false;
+  }
+  return bwd.G == 1;
+}
+
 int64_t canonical_param_count(const ModelDims& md) {
   const int64_t L = md.L, H = md.H;
   const int64_t phi_out = md.multi ? L : 1;
@@ -274,7 +282,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     const size_t nst = (size_t)(4 + md.L) * row_stride(plan->Ns * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
-    const ActLayout al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, fwd.G);
+    const ActLayout al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, fwd.G, act_grid_major(bwd));
     w.act = o; o = align(o + (size_t)fwd.nbatch * md.K * (size_t)al.total * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * make_frag_layout(md.L, md.H).step * 4);   // one block per warp
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
