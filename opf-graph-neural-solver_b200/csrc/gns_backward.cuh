@@ -3,7 +3,7 @@
 //
 // Per step k = K-1 .. 0 (state_k = checkpoint written by the forward kernel):
 //   1. physics adjoint: loss -> dP' -> (lambda / p_global coupling, line flows) -> v', theta'.
-//      All scatter-adds of the forward become CSR gathers here, so there are no atomics.
+//      All scatter-adds of the forward become CSR gathers here, so there are no scatter atomics.
 //   2. MLP adjoint per bus, thread-local: the bus thread reads the hidden activations the
 //      forward kernel kept (ActLayout: post-LeakyReLU values, whose sign gives the slope) and
 //      back-propagates them (dX), mirroring the bus-centric forward.  Nothing is recomputed.
