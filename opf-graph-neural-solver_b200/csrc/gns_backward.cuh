@@ -20,9 +20,6 @@
 
 namespace gns {
 
-#ifndef GNS_BWD_L2PREFETCH
-#define GNS_BWD_L2PREFETCH 1
-#endif
 #ifndef GNS_KTS
 #define GNS_KTS 48
 #endif
@@ -353,13 +350,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 
     for (int k = K - 1; k >= 0; --k) {
       // ---------------- stage weights and state_k ----------------
-#if GNS_BWD_L2PREFETCH
-      {   // pull this warp's step-k accumulator block towards L2 now; the read-modify-writes of the
-          // weight-gradient tiles then see L2 latency instead of DRAM latency
-        const char* blk = reinterpret_cast<const char*>(gacc_w + (size_t)k * FL.step);
-        for (int i = lane * 128; i < FL.step * 4; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
-      }
-#endif
       if (bus_on) {
         if (k >= 1) {
           const float* ck = ck_base + (size_t)(k - 1) * ck_stride + (size_t)n * a.Gf;
@@ -488,21 +478,6 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
       // adjv / adjth now hold d loss / d v', d theta' of this thread's bus (registers).
 
       // ---------------- MLP adjoint + weight gradients (bus-centric, warp tiles) ----------------
-      {   // pull what the next step (or the next batch) loads first towards L2 while this phase computes
-        if (k >= 2) {
-          const char* nx = reinterpret_cast<const char*>(a.ckpt + ((size_t)bf * K + (k - 2)) * ck_stride);
-          for (int i = tid * 128; i < (int)(ck_stride * 4); i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
-        } else if (k == 0 && batch + (int)gridDim.x < a.nbatch) {
-          const long long gn = (long long)(batch + gridDim.x) * G;
-          const char* pb = reinterpret_cast<const char*>(a.buses + gn * N * 6);
-          const char* pl = reinterpret_cast<const char*>(a.lines + gn * E * 7);
-          for (int i = tid * 128; i < G * N * 24; i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
-          for (int i = tid * 128; i < G * E * 28; i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + i));
-          const long long bfn = ((gn < a.S ? gn : a.S - 1)) / a.Gf;
-          const char* nx = reinterpret_cast<const char*>(a.ckpt + ((size_t)bfn * K + (K - 2 >= 0 ? K - 2 : 0)) * ck_stride);
-          for (int i = tid * 128; i < (int)(ck_stride * 4); i += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
-        }
-      }
       mbar_wait(s_mbar, w_phase);                      // this step's weights have landed
       w_phase ^= 1;
       float* const gk = gacc_w + (size_t)k * FL.step;

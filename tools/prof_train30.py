@@ -1,0 +1,17 @@
+"""Small fwd+bwd run of case30 (8 grids per backward CTA) for profiling."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import opf_graph_neural_solver_b200 as pkg
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 9472
+torch.manual_seed(0)
+model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+model.validate_topology = False
+b, l, g, _ = pkg.data.make_batch(30, S, seed=1)
+b, l, g = b.cuda(), l.cuda(), g.cuda()
+for _ in range(3):
+    model.zero_grad(set_to_none=True)
+    out = model(b, l, g, *pkg.get_BLG())
+    out[2].mean().backward()
+torch.cuda.synchronize()
+print("ok", float(out[2].mean().detach()))
