@@ -41,8 +41,11 @@ struct BwdSmem {          // offsets in floats from SmemPlan.extra
 // interleaved for the MMA A fragment: [pair p = c % 8][item][c / 8] with row stride kSA, so one LDS.128 at
 // item a yields {c[a], c+8[a], c[a+1], c+8[a+1]} = (a0, a1, a2, a3) of an m16n8k8 with k slots (t, t+4) =
 // items (a, a+1): no register shuffling in front of the HMMA.
+#ifndef GNS_AMREG_MAX_L
+#define GNS_AMREG_MAX_L 32   // latents up to this size keep a step's adj m additions in registers
+#endif
 #ifndef GNS_MMA_CHAINS
-#define GNS_MMA_CHAINS 2   // 2 vs 4 chains: identical time (measured), 2 saves registers
+#define GNS_MMA_CHAINS 2   // measured on case300 training: 1 chain 23.8 ms, 2 chains 22.9 ms, 4 chains 24.9 ms (registers)
 #endif
 constexpr int kSA = 68;   // 64 + 4: the 8 lanes of a 128-bit phase (2 pair rows x 4 quads 8 floats apart) hit 32 distinct banks
 __host__ __device__ constexpr int bwd_hid_floats() { return 8 * kSA; }
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         for (int o = 0; o < H; ++o) adjA[o] = 0.f;
         // small latents: this step's additions to adj m stay in registers and are folded in once at the end
         // (the only readers of adj m' inside the step, the m-net output layer and its tile, come first)
-        constexpr bool AMREG = (L <= 32);
+        constexpr bool AMREG = (L <= GNS_AMREG_MAX_L);
         float amr[AMREG ? L : 1];
 #pragma unroll
         for (int i = 0; i < (AMREG ? L : 1); ++i) amr[i] = 0.f;
