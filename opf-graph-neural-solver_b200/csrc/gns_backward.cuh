@@ -12,8 +12,8 @@
 //      memory tile and runs the 32-item product on the tensor cores (mma.sync m16n8k8 TF32 with
 //      a 3-term split that keeps FP32 accuracy).  State rows (v, theta, dP, dQ, m, adj m) are
 //      already stored [feature][item] and are read in place as B fragments.  The accumulator
-//      cells go to a per-warp private block in global memory in fragment order (one 128-bit
-//      reduction per lane and 8-row tile, L2 resident), summed over warps and re-ordered by a
+//      cells go to a per-warp private block in global memory in fragment order (one or two 64-bit
+//      reductions per lane and 8-row tile, L2 resident), summed over warps and re-ordered by a
 //      second small kernel: deterministic, no contended atomics.
 #pragma once
 #include "gns_common.cuh"
