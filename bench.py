@@ -349,8 +349,8 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": gps_e2e, "unit": "grids/s", "h2d_bytes_per_step": S * in_b, "d2h_bytes_per_step": S * out_b,
                 "ms_per_step": ms_e2e, "path": "pinned host tensors -> GNS.infer_host (8192-grid chunks, copy/compute overlap) -> pinned host outputs"},
-        # our kernels per call: forward = pack, fuse, gns_forward; backward = gns_backward, reduce, unfuse, unpack
-        "gpu_launches": 3 * args.steps + 7 * args.steps + max(2, args.steps // 2) * 3 * ((S + 8191) // 8192),
+        # our kernels per call: forward = pack, fuse, gns_forward; backward = gns_backward, reduce, gather, unfuse, unpack
+        "gpu_launches": 3 * args.steps + 8 * args.steps + max(2, args.steps // 2) * 3 * ((S + 8191) // 8192),
         "clocks": clocks,
     }
     line["config"]["numa_bound"] = numa_bound

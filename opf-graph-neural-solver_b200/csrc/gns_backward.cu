@@ -79,26 +79,42 @@ static const int32_t* get_frag_map(gns_plan* plan, const ModelDims& md) {
   return d;
 }
 
-// packed_grad[k][p] = sum_w gacc[w][k][inv[p]]   (0 where inv[p] < 0)
-__global__ void reduce_partials_kernel(const float* __restrict__ gacc, const int32_t* __restrict__ inv,
-                                       float* __restrict__ packed, int K, int wstep, int fstep, int nparts) {
-  const long long n = (long long)K * wstep, part = (long long)K * fstep;
+// fragsum[f] = sum_w gacc[w][f] over the per-warp accumulator blocks, in fragment order: consecutive threads read
+// consecutive floats of one block (coalesced), 16 part lanes per block split the blocks between them and are folded
+// in a fixed order (deterministic).  A block covers 64 cells: 264 CTAs for K=4 on case-sized models.
+constexpr int kRedF = 64, kRedP = 16;
+__global__ void __launch_bounds__(kRedF * kRedP) reduce_partials_kernel(const float* __restrict__ gacc, float* __restrict__ fragsum,
+                                                                        long long n, int nparts) {
+  __shared__ float sm[kRedP][kRedF];
+  const int fx = threadIdx.x, py = threadIdx.y;
+  const long long f = blockIdx.x * (long long)kRedF + fx;
+  float s0 = 0.f, s1 = 0.f;
+  if (f < n) {
+    int w = py;
+    for (; w + kRedP < nparts; w += 2 * kRedP) {
+      s0 += gacc[(size_t)w * n + f];
+      s1 += gacc[(size_t)(w + kRedP) * n + f];
+    }
+    if (w < nparts) s0 += gacc[(size_t)w * n + f];
+  }
+  sm[py][fx] = s0 + s1;
+  __syncthreads();
+  if (py == 0 && f < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRedP; ++j) t += sm[j][fx];
+    fragsum[f] = t;
+  }
+}
+
+// packed[k][p] = fragsum[k][inv[p]]   (0 where inv[p] < 0): fragment order -> packed parameter layout
+__global__ void gather_frag_kernel(const float* __restrict__ fragsum, const int32_t* __restrict__ inv,
+                                   float* __restrict__ packed, int K, int wstep, int fstep) {
+  const long long n = (long long)K * wstep;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(p / wstep);
     const int f = inv[p - (long long)k * wstep];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (f >= 0) {
-      const float* src = gacc + (size_t)k * fstep + f;
-      int w = 0;
-      for (; w + 3 < nparts; w += 4) {
-        s0 += src[(size_t)w * part];
-        s1 += src[(size_t)(w + 1) * part];
-        s2 += src[(size_t)(w + 2) * part];
-        s3 += src[(size_t)(w + 3) * part];
-      }
-      for (; w < nparts; ++w) s0 += src[(size_t)w * part];
-    }
-    packed[p] = (s0 + s1) + (s2 + s3);
+    packed[p] = f >= 0 ? fragsum[(size_t)k * fstep + f] : 0.f;
   }
 }
 
@@ -211,8 +227,10 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   if (e != cudaSuccess) { set_error(std::string("backward launch: ") + cudaGetErrorString(e)); return -2; }
   {
     const int th = 256;
+    float* fragsum = reinterpret_cast<float*>(wsb + ws.fragsum);
+    reduce_partials_kernel<<<(unsigned)((per_part + kRedF - 1) / kRedF), dim3(kRedF, kRedP), 0, st>>>(gacc, fragsum, (long long)per_part, nparts);
     const int bl = (int)std::min<long long>(((long long)md.K * W.wstep + th - 1) / th, 2048);
-    reduce_partials_kernel<<<bl, th, 0, st>>>(gacc, d_inv, packed_grad, md.K, W.wstep, FL.step, nparts);
+    gather_frag_kernel<<<bl, th, 0, st>>>(fragsum, d_inv, packed_grad, md.K, W.wstep, FL.step);
     const int nphi = md.multi ? 3 : 1, PO = md.multi ? md.L : 1;
     const int tot = md.K * (nphi * PO * md.H + nphi * PO + 3 * PO * md.H);
     unfuse_grads_kernel<<<(tot + th - 1) / th, th, 0, st>>>(packed_grad, a.params, W, md.K);

@@ -56,6 +56,7 @@ struct Workspace {
   size_t pglob = 0;           // [nbatch][K][G] floats                 (need_grad)
   size_t act = 0;             // [nbatch][K][ActLayout.total] floats   (need_grad): hidden activations
   size_t gpartial = 0;        // [ctas*nwarps][K][FragLayout.step] floats (need_grad): per-warp gradient partial sums
+  size_t fragsum = 0;         // [K][FragLayout.step] floats           (need_grad): accumulators summed over warps
   size_t packed_grad = 0;     // [K][wstep] floats                     (need_grad)
   size_t mscratch = 0;        // [ctas][2][L][NGs] floats              (need_grad, L > 32)
   size_t total = 0;

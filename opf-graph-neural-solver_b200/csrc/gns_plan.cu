@@ -285,6 +285,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     const ActLayout al = make_act_layout(md.H, md.multi ? 3 : 1, plan->Ns, plan->E, fwd.G, act_grid_major(bwd));
     w.act = o; o = align(o + (size_t)fwd.nbatch * md.K * (size_t)al.total * 4);
     w.gpartial = o; o = align(o + (size_t)bwd.ctas * (bwd.T / 32) * md.K * make_frag_layout(md.L, md.H).step * 4);   // one block per warp
+    w.fragsum = o; o = align(o + (size_t)md.K * make_frag_layout(md.L, md.H).step * 4);
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
     if (md.L > 32) { w.mscratch = o; o = align(o + (size_t)bwd.ctas * 2 * md.L * bwd_bus_stride(plan->Ns * bwd.G) * 4); }
   }
