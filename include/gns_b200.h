@@ -101,19 +101,27 @@ int gns_backward(const gns_plan* plan, const float* params,
 int gns_check_topology(const gns_plan* plan, const float* lines, const float* gens,
                        int64_t S, void* stream);
 
-/* Launch geometry chosen for this plan/model (for bench/roofline reporting):
- * out[0]=grids per CTA, out[1]=threads per CTA, out[2]=dynamic smem bytes,
- * out[3]=CTAs launched for S grids, out[4]=vector width (grids per thread). */
+/* Same check without synchronisation: ORs 1 into the caller's device int `flag` (zeroed by the caller) when a grid
+ * of the batch carries another topology; the caller reads the flag when it next synchronises (pipelined host
+ * batches check every chunk this way).  Replaces the per-sample index rebuild of ref GNS/main.py:153. */
+int gns_check_topology_async(const gns_plan* plan, const float* lines, const float* gens,
+                             int64_t S, int* flag, void* stream);
+
 /* Layout maps of the gradient path, for tests and tools (host only, no GPU needed).
  *   "pack": canonical (state_dict order, all K steps) index -> packed index        [gns_param_count]
  *   "frag": packed index inside ONE step's block -> index inside that step's fragment-order
  *           accumulator block of gns_backward, or -1 (padding, and the W4 / b4 / W1-slice entries the
  *           fused block's chain rule fills in)                                      [packed step size]
+ *   "frag2": the same map for the warp-specialised backward kernel (large grids)    [packed step size]
  * Returns the number of entries (writes them when out != NULL and capacity suffices), -1 on error.
  * Replaces nothing in the reference: autograd keeps its own bookkeeping (ref GNS/main.py:288). */
 int gns_layout_export(const char* name, int K, int latent_dim, int hidden_dim, int multiple_phi,
                       int32_t* out, int capacity);
 
+/* Launch geometry chosen for this plan/model (for bench/roofline reporting; nothing in the reference corresponds):
+ * out[0]=grids per CTA, out[1]=threads per CTA, out[2]=dynamic smem bytes, out[3]=CTAs launched for S grids
+ * (persistent kernels: min(batches, SMs x resident CTAs)), out[4]=items per thread (grids, or bus slots in the
+ * warp-specialised backward kernel), out[5]=CTA batches, out[6]=SMs, out[7]=launch-bounds variant. */
 int gns_launch_info(const gns_plan* plan, int64_t S, int K, int latent_dim, int hidden_dim,
                     int multiple_phi, int backward, int32_t out[8]);
 

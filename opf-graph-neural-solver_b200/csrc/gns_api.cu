@@ -152,7 +152,8 @@ extern "C" int64_t gns_workspace_bytes(const gns_plan* plan, int64_t S, int K, i
     if (!choose_geometry(plan, md, S, true, &gb)) return -1;
     gb.ctas = backward_ctas(plan, md, gb);
   }
-  return (int64_t)plan_workspace(plan, md, S, need_grad != 0, gf, gb).total;
+  const Bwd2Geom b2 = need_grad ? choose_bwd2(plan, md, S) : Bwd2Geom{};
+  return (int64_t)plan_workspace(plan, md, S, need_grad != 0, gf, gb, b2).total;
 }
 
 extern "C" int gns_launch_info(const gns_plan* plan, int64_t S, int K, int L, int H, int multi, int backward, int32_t out[8]) {
@@ -161,7 +162,19 @@ extern "C" int gns_launch_info(const gns_plan* plan, int64_t S, int K, int L, in
   if (!check_model(md)) return -1;
   Geometry g;
   if (!choose_geometry(plan, md, S, backward != 0, &g)) return -1;
-  const int ctas = backward ? backward_ctas(plan, md, g) : std::min(g.nbatch, plan->num_sms * 8);
+  // persistent kernels: CTAs = min(batches, SMs x CTAs resident per SM); residency from shared memory and the
+  // register budget of the launch-bounds variant (the launchers clamp with the occupancy API, same numbers)
+  const int regs = g.tmax == 320 ? 200 : (g.tmax == 384 ? 168 : 64);
+  const int per_sm = std::max(1, std::min((int)((size_t)233472 / (g.smem_bytes + 1024)), 65536 / (g.T * regs)));
+  int ctas = backward ? std::min(backward_ctas(plan, md, g), plan->num_sms * per_sm) : std::min(g.nbatch, plan->num_sms * per_sm);
+  if (backward) {
+    const Bwd2Geom b2 = choose_bwd2(plan, md, S);
+    if (b2.ok) {   // warp-specialised kernel: one grid per CTA at a time
+      out[0] = 1; out[1] = b2.T; out[2] = (int32_t)b2.smem_bytes; out[3] = b2.ctas; out[4] = 2;
+      out[5] = (int32_t)std::min<int64_t>(S, 2147483647); out[6] = plan->num_sms; out[7] = 384;
+      return 0;
+    }
+  }
   out[0] = g.G; out[1] = g.T; out[2] = (int32_t)g.smem_bytes; out[3] = ctas; out[4] = g.VG;
   out[5] = g.nbatch; out[6] = plan->num_sms; out[7] = g.tmax;
   return 0;
@@ -187,7 +200,8 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
     if (!choose_geometry(plan, md, S, true, &gb)) return -1;
     gb.ctas = backward_ctas(plan, md, gb);
   }
-  const Workspace ws = plan_workspace(plan, md, S, need_grad != 0, gf, gb);
+  const Bwd2Geom b2 = need_grad ? choose_bwd2(plan, md, S) : Bwd2Geom{};
+  const Workspace ws = plan_workspace(plan, md, S, need_grad != 0, gf, gb, b2);
   if ((int64_t)ws.total > workspace_bytes) {
     set_error("gns_forward: workspace too small (" + std::to_string(workspace_bytes) + " < " + std::to_string(ws.total) + ")");
     return -1;
@@ -218,8 +232,10 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = K; a.NGQ = gf.NGQ; a.G = gf.G; a.nbatch = gf.nbatch;
   a.NGs = row_stride(plan->Ns * gf.G); a.EGs = row_stride(plan->E * gf.G);
-  a.need_grad = need_grad ? 1 : 0;
-  a.al = make_act_layout(H, multi ? 3 : 1, plan->Ns, plan->E, gf.G, need_grad ? act_grid_major(gb) : true);
+  a.need_grad = need_grad ? (b2.ok ? 2 : 1) : 0;     // 2: per-grid block checkpoints (Act2Layout) for gns_backward2
+  a.a2 = b2.a2;
+  a.ck2 = a.ckpt;
+  a.al = make_act_layout(H, multi ? 3 : 1, plan->Ns, plan->E, gf.G, (need_grad && !b2.ok) ? act_grid_major(gb) : true);
   a.use_tma = (gf.sm.stage_l != 0 && ((uintptr_t)buses % 16 == 0) && ((uintptr_t)lines % 16 == 0) &&
                ((uintptr_t)gens % 16 == 0)) ? 1 : 0;
   std::memcpy(a.grp_of_warp, gf.grp_of_warp, 32);
@@ -262,6 +278,19 @@ extern "C" int gns_check_topology(const gns_plan* plan, const float* lines, cons
     set_error(std::string("gns_check_topology: ") + cudaGetErrorString(cudaGetLastError())); return -2;
   }
   return flag ? 1 : 0;
+}
+
+extern "C" int gns_check_topology_async(const gns_plan* plan, const float* lines, const float* gens, int64_t S, int* flag,
+                                        void* stream) {
+  if (!plan || !lines || (plan->Gn > 0 && !gens) || S <= 0 || !flag) { set_error("gns_check_topology_async: bad arguments"); return -1; }
+  if (!check_plan(plan)) return -1;
+  if (cudaSetDevice(plan->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return -2; }
+  const long long total = S * (2LL * plan->E + plan->Gn);
+  const int th = 256;
+  const int bl = (int)std::min<long long>((total + th - 1) / th, 4096);
+  check_topology_kernel<<<bl, th, 0, (cudaStream_t)stream>>>(lines, gens, plan->d_expect, S, plan->E, plan->Gn, flag);
+  if (cudaGetLastError() != cudaSuccess) { set_error("gns_check_topology_async: launch failed"); return -2; }
+  return 0;
 }
 
 extern "C" int gns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "gns_backward.cuh"
+#include "gns_backward2.cuh"
 #include "gns_host.h"
 #include "../../include/gns_b200.h"
 
@@ -17,6 +18,10 @@ int backward_extra_floats(int N, int E, int G, int L, int H, int T) {
   return make_bwd_smem(N, E, G, L, H, L, T / 32, L > 32).total;
 }
 
+int make_bwd2_smem_floats(int L, int H, int E, int wstep, const Act2Layout& a2) {
+  return make_bwd2_smem(L, H, E, wstep, a2).total;
+}
+
 int backward_ctas(const gns_plan* plan, const ModelDims&, const Geometry& g) {
   // one persistent CTA per SM slot; the exact occupancy is clamped again at launch
   return std::min(g.nbatch, plan->num_sms * std::max(1, (int)(plan->smem_optin / std::max<size_t>(g.smem_bytes, 1))));
@@ -26,7 +31,9 @@ int backward_ctas(const gns_plan* plan, const ModelDims&, const Geometry& g) {
 // block (FragLayout), or -1 for padding and for the entries the backward kernel never writes (W4 / b4 and
 // the W1 slice behind the fused block, which unfuse_grads_kernel derives).  Mirrors the GEMM calls of
 // gns_backward_kernel one to one.
-std::vector<int32_t> build_frag_map(const ModelDims& md) {
+// `v2`: the warp-specialised kernel computes the scalar nets' output layer with the roles swapped (hid = [h2, 1],
+// one wide row = the output adjoint), so its cells are (row 0, column c) instead of (row r, column 0).
+std::vector<int32_t> build_frag_map(const ModelDims& md, bool v2) {
   const int L = md.L, H = md.H;
   const bool multi = md.multi != 0;
   const WLayout W = make_wlayout(L, H, multi);
@@ -46,7 +53,8 @@ std::vector<int32_t> build_frag_map(const ModelDims& md) {
     }
     const int lb = W.off_ln[0] + q * W.ln_size_s;
     if (q < 2) {
-      for (int r = 0; r < H + 1; ++r) put(lb + (r < H ? W.ln_wo + r : W.ln_bo_s), fb + F.out + frag_index(r, 0));
+      for (int r = 0; r < H + 1; ++r)
+        put(lb + (r < H ? W.ln_wo + r : W.ln_bo_s), fb + F.out + (v2 ? frag_index(0, r) : frag_index(r, 0)));
     } else {
       for (int r = 0; r < L; ++r)
         for (int c = 0; c < H + 1; ++c) put(lb + (c < H ? W.ln_wo + r * W.HP + c : W.ln_bo_m + r), fb + F.out + frag_index(r, c));
@@ -64,11 +72,11 @@ std::vector<int32_t> build_frag_map(const ModelDims& md) {
   return inv;
 }
 
-static const int32_t* get_frag_map(gns_plan* plan, const ModelDims& md) {
-  auto key = std::make_tuple(md.L, md.H, md.multi);
+static const int32_t* get_frag_map(gns_plan* plan, const ModelDims& md, bool v2) {
+  auto key = std::make_tuple(md.L, md.H, md.multi + (v2 ? 2 : 0));
   auto it = plan->frag_maps.find(key);
   if (it != plan->frag_maps.end()) return it->second;
-  const std::vector<int32_t> inv = build_frag_map(md);
+  const std::vector<int32_t> inv = build_frag_map(md, v2);
   int32_t* d = nullptr;
   if (cudaMalloc(&d, inv.size() * sizeof(int32_t)) != cudaSuccess ||
       cudaMemcpy(d, inv.data(), inv.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -167,6 +175,66 @@ __global__ void unpack_grads_kernel(const float* __restrict__ packed, const int3
     canon[i] = packed[map[i]];
 }
 
+// fragment-order accumulators -> state_dict-order gradient (shared by both backward kernels)
+static int fold_gradients(gns_plan* plan, const ModelDims& md, const float* gacc, int nparts, const int32_t* d_inv,
+                          const float* packed_params, char* wsb, const Workspace& ws, float* grad_params, cudaStream_t st) {
+  const gns_plan::PackMap* pm = get_pack_map(plan, md);
+  if (!pm) return -2;
+  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
+  const FragLayout FL = make_frag_layout(md.L, md.H);
+  const size_t per_part = (size_t)md.K * FL.step;
+  float* packed_grad = reinterpret_cast<float*>(wsb + ws.packed_grad);
+  const int th = 256;
+  float* fragsum = reinterpret_cast<float*>(wsb + ws.fragsum);
+  reduce_partials_kernel<<<(unsigned)((per_part + kRedF - 1) / kRedF), dim3(kRedF, kRedP), 0, st>>>(gacc, fragsum, (long long)per_part, nparts);
+  const int bl = (int)std::min<long long>(((long long)md.K * W.wstep + th - 1) / th, 2048);
+  gather_frag_kernel<<<bl, th, 0, st>>>(fragsum, d_inv, packed_grad, md.K, W.wstep, FL.step);
+  const int nphi = md.multi ? 3 : 1, PO = md.multi ? md.L : 1;
+  const int tot = md.K * (nphi * PO * md.H + nphi * PO + 3 * PO * md.H);
+  unfuse_grads_kernel<<<(tot + th - 1) / th, th, 0, st>>>(packed_grad, packed_params, W, md.K);
+  const int bl2 = (int)std::min<long long>((pm->n_canon + th - 1) / th, 1024);
+  unpack_grads_kernel<<<bl2, th, 0, st>>>(packed_grad, pm->d_map, grad_params, pm->n_canon);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("gradient reduce: ") + cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+// warp-specialised kernel (large grids, see gns_backward2.cuh)
+static int run_backward2(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2, const Workspace& ws, const float* buses,
+                         const float* lines, const float* gens, long long S, float gamma, const float* grad_total,
+                         const float* grad_last, const float* grad_v, const float* grad_theta, float* grad_params,
+                         char* wsb, cudaStream_t st) {
+  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
+  const FragLayout FL = make_frag_layout(md.L, md.H);
+  const size_t per_part = (size_t)md.K * FL.step;
+  const int32_t* d_inv = get_frag_map(plan, md, true);
+  if (!d_inv) return -2;
+  const int nparts = b2.ctas * b2.CW;
+  float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
+  cudaError_t e = cudaMemsetAsync(gacc, 0, (size_t)nparts * per_part * 4, st);
+  if (e != cudaSuccess) { set_error(std::string("memset gacc: ") + cudaGetErrorString(e)); return -2; }
+  Bwd2Launcher launch = find_backward2(md.L, md.H, md.multi);
+  if (!launch) { set_error("gns_backward: warp-specialised kernel not built for these dims"); return -1; }
+  Bwd2Args a{};
+  a.params = reinterpret_cast<const float*>(wsb + ws.packed_params);   // packed by gns_forward
+  a.buses = buses; a.lines = lines; a.gens = gens;
+  a.ck2 = reinterpret_cast<const float*>(wsb + ws.ckpt);
+  a.pglob = reinterpret_cast<const float*>(wsb + ws.pglob);
+  a.act = reinterpret_cast<const float*>(wsb + ws.act);
+  a.grad_total = grad_total; a.grad_last = grad_last; a.grad_v = grad_v; a.grad_theta = grad_theta;
+  a.gacc = gacc;
+  a.topo = plan->d_topo;
+  a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K;
+  a.PW = b2.PW; a.CW = b2.CW; a.maxwalk = plan->max_walk;
+  a.a2 = b2.a2;
+  a.sm = make_bwd2_smem(md.L, md.H, plan->E, W.wstep, b2.a2);
+  a.to = plan->to;
+  for (int k = 0; k < md.K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(md.K - k));
+  e = launch(a, b2, plan->num_sms, st);
+  if (e != cudaSuccess) { set_error(std::string("backward2 launch: ") + cudaGetErrorString(e)); return -2; }
+  return fold_gradients(plan, md, gacc, nparts, d_inv, a.params, wsb, ws, grad_params, st);
+}
+
 int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const float* buses, const float* lines,
                  const float* gens, long long S, float gamma, const float* grad_total, const float* grad_last,
                  const float* grad_v, const float* grad_theta, float* grad_params, void* workspace,
@@ -176,16 +244,19 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   if (!choose_geometry(plan, md, S, false, &gf)) return -1;
   if (!choose_geometry(plan, md, S, true, &gb)) return -1;
   gb.ctas = backward_ctas(plan, md, gb);
-  const Workspace ws = plan_workspace(plan, md, S, true, gf, gb);
+  const Bwd2Geom b2 = choose_bwd2(plan, md, S);
+  const Workspace ws = plan_workspace(plan, md, S, true, gf, gb, b2);
+  if (b2.ok) {
+    if ((long long)ws.total > workspace_bytes) { set_error("gns_backward: workspace too small"); return -1; }
+    return run_backward2(plan, md, b2, ws, buses, lines, gens, S, gamma, grad_total, grad_last, grad_v, grad_theta,
+                         grad_params, static_cast<char*>(workspace), st);
+  }
   if ((long long)ws.total > workspace_bytes) { set_error("gns_backward: workspace too small"); return -1; }
-  const gns_plan::PackMap* pm = get_pack_map(plan, md);
-  if (!pm) return -2;
-  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
   char* wsb = static_cast<char*>(workspace);
   const int nwarps = gb.T / 32;
   const FragLayout FL = make_frag_layout(md.L, md.H);
   const size_t per_part = (size_t)md.K * FL.step;
-  const int32_t* d_inv = get_frag_map(plan, md);
+  const int32_t* d_inv = get_frag_map(plan, md, false);
   if (!d_inv) return -2;
   // GNS_DETERMINISTIC=0: the warps of a CTA share one accumulator block (10x smaller, L2 resident); the order of
   // their floating-point reductions is then not fixed, so gradients are reproducible to rounding only
@@ -193,7 +264,6 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   const bool per_warp = !(det_env && det_env[0] == '0');
   const int nparts = gb.ctas * (per_warp ? nwarps : 1);
   float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
-  float* packed_grad = reinterpret_cast<float*>(wsb + ws.packed_grad);
   cudaError_t e = cudaMemsetAsync(gacc, 0, (size_t)nparts * per_part * 4, st);
   if (e != cudaSuccess) { set_error(std::string("memset gacc: ") + cudaGetErrorString(e)); return -2; }
 
@@ -225,21 +295,7 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   for (int k = 0; k < md.K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(md.K - k));
   e = launch(a, gb, st);
   if (e != cudaSuccess) { set_error(std::string("backward launch: ") + cudaGetErrorString(e)); return -2; }
-  {
-    const int th = 256;
-    float* fragsum = reinterpret_cast<float*>(wsb + ws.fragsum);
-    reduce_partials_kernel<<<(unsigned)((per_part + kRedF - 1) / kRedF), dim3(kRedF, kRedP), 0, st>>>(gacc, fragsum, (long long)per_part, nparts);
-    const int bl = (int)std::min<long long>(((long long)md.K * W.wstep + th - 1) / th, 2048);
-    gather_frag_kernel<<<bl, th, 0, st>>>(fragsum, d_inv, packed_grad, md.K, W.wstep, FL.step);
-    const int nphi = md.multi ? 3 : 1, PO = md.multi ? md.L : 1;
-    const int tot = md.K * (nphi * PO * md.H + nphi * PO + 3 * PO * md.H);
-    unfuse_grads_kernel<<<(tot + th - 1) / th, th, 0, st>>>(packed_grad, a.params, W, md.K);
-    const int bl2 = (int)std::min<long long>((pm->n_canon + th - 1) / th, 1024);
-    unpack_grads_kernel<<<bl2, th, 0, st>>>(packed_grad, pm->d_map, grad_params, pm->n_canon);
-  }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error(std::string("gradient reduce: ") + cudaGetErrorString(e)); return -2; }
-  return 0;
+  return fold_gradients(plan, md, gacc, nparts, d_inv, a.params, wsb, ws, grad_params, st);
 }
 
 }  // namespace gns
@@ -254,7 +310,8 @@ extern "C" int gns_layout_export(const char* name, int K, int latent_dim, int hi
   std::vector<int32_t> v;
   const std::string n(name);
   if (n == "pack") v = build_pack_map(md);
-  else if (n == "frag") v = build_frag_map(md);
+  else if (n == "frag") v = build_frag_map(md, false);
+  else if (n == "frag2") v = build_frag_map(md, true);
   else { set_error("gns_layout_export: unknown map '" + n + "'"); return -1; }
   if (out) {
     if (capacity < (int)v.size()) { set_error("gns_layout_export: capacity too small"); return -1; }

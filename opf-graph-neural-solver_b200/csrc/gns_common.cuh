@@ -158,6 +158,43 @@ __host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, in
 }
 
 // ---------------------------------------------------------------------------------
+// Checkpoints for the warp-specialised backward kernel (gns_backward2.cuh, one grid per CTA): everything a
+// (grid, step) needs is contiguous, every block is [row][item] with a row stride = 16 mod 32 floats (the MMA
+// fragment loads of 8 rows x 4 quads are conflict-free once a block sits in shared memory), so a block moves
+// with ONE bulk copy (cp.async.bulk).  Bus blocks are indexed by BUS RANK (no twin columns), line blocks by
+// the plan's in_pos column.  Per pair q:  h2L, h1L, A (H rows x NbP each), h1 of the phi net per line
+// (H rows x EP), and the LeakyReLU slope bits: row 0 = bits of (h1L, h2L) per slot, row 1+it = bits of
+// (h1, h2) of the it-th line the slot walks (bit o: h1[o] > 0, bit H+o: h2[o] > 0), MR = 1 + max walk rows x NsM.
+// The forward zero-fills the padding columns of the float blocks (0 x garbage must not be NaN).
+// ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int mma_stride(int items) {
+  int p = pad4(items);
+  while (p % 32 != 16) p += 4;
+  return p;
+}
+struct Act2Layout {
+  int NbP, EP, NsM, MR;
+  int h2L[3], h1L[3], A[3], h1line[3], mask[3];
+  int step;               // floats per (grid, step)
+  int state;              // floats per state checkpoint: (4+L) * NbP
+};
+__host__ __device__ inline Act2Layout make_act2_layout(int L, int H, int N, int Ns, int E, int maxwalk) {
+  Act2Layout a{};
+  a.NbP = mma_stride(N); a.EP = mma_stride(E); a.NsM = pad4(Ns); a.MR = 1 + maxwalk;
+  int o = 0;
+  for (int q = 0; q < 3; ++q) {
+    a.h2L[q] = o; o += H * a.NbP;
+    a.h1L[q] = o; o += H * a.NbP;
+    a.A[q] = o; o += H * a.NbP;
+    a.h1line[q] = o; o += H * a.EP;
+    a.mask[q] = o; o += a.MR * a.NsM;
+  }
+  a.step = o;
+  a.state = (4 + L) * a.NbP;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------
 // Topology index block (shared by all grids; copied to shared memory once per CTA).
 // All entries are uint16 (n_bus, n_line < 65536).
 // ---------------------------------------------------------------------------------
@@ -179,7 +216,12 @@ struct TopoOffsets {      // offsets in uint16 units inside the index block
   int prim_of;            // [Ns] primary slot of the slot's bus
   int gsz;                // [Ns] slots in this bus's twin group (1, 2 or 4), aligned to gsz
   int rank_of;            // [N]  primary slot of external bus
-  int total;              // padded to a multiple of 8
+  int brank;              // [Ns] bus rank (position in the degree-descending bus order, 0..N-1) of the slot's bus
+  int total;              // padded to a multiple of 8: what the forward / first backward kernel copy to shared memory
+  // extension read by the warp-specialised backward kernel only (gns_backward2.cuh)
+  int fr, tr;             // [E] bus rank of the from / to bus
+  int ext_rank;           // [N] bus rank -> external bus
+  int total_ext;          // padded to a multiple of 8
 };
 
 __host__ __device__ inline TopoOffsets make_topo_offsets(int N, int Ns, int E, int Gn) {
@@ -204,7 +246,13 @@ __host__ __device__ inline TopoOffsets make_topo_offsets(int N, int Ns, int E, i
   t.prim_of = o; o += Ns;
   t.gsz = o; o += Ns;
   t.rank_of = o; o += N;
+  t.brank = o; o += Ns;
   t.total = (o + 7) & ~7;
+  o = t.total;
+  t.fr = o; o += E;
+  t.tr = o; o += E;
+  t.ext_rank = o; o += N;
+  t.total_ext = (o + 7) & ~7;
   return t;
 }
 
@@ -280,6 +328,14 @@ __device__ __forceinline__ void add_vec(float (&a)[VG], const float (&b)[VG]) {
 #pragma unroll
     for (int g = 0; g < VG; ++g) a[g] += b[g];
   }
+}
+// LeakyReLU slope bits of the post-activation values h (h > 0 <=> z > 0): bit (shift + o) of w[g] is set where the slope is 1
+template <int H, int VG>
+__device__ __forceinline__ void slope_bits(uint32_t (&w)[VG], const float (&h)[H][VG], int shift) {
+#pragma unroll
+  for (int o = 0; o < H; ++o)
+#pragma unroll
+    for (int g = 0; g < VG; ++g) w[g] |= (h[o][g] > 0.f) ? (1u << (shift + o)) : 0u;
 }
 __device__ __forceinline__ float lrelu_grad(float z) { return z > 0.f ? 1.f : kSlope; }   // also valid on h = lrelu(z)
 
@@ -484,6 +540,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n\t}"
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier over a subset of the CTA's warps (id 1..15; `count` = participating threads, a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 // global -> shared bulk copy (16-byte aligned addresses and size), completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -630,6 +693,8 @@ struct FwdArgs {
   int NGs, EGs;            // padded row strides of the [.][Ns][G] and [.][E][G] arrays
   int need_grad;
   ActLayout al;
+  Act2Layout a2;           // GRADV = 3: per-grid checkpoints for the warp-specialised backward kernel
+  float* ck2;              // [S][K+1][a2.state] state entering step k (k = 0..K-1) and the final state (K)
   int use_tma;             // inputs 16-byte aligned and staging present: prefetch the next batch with cp.async.bulk
   unsigned char grp_of_warp[32];   // warp -> group of 32/NGQ consecutive bus slots
   SmemPlan sm;

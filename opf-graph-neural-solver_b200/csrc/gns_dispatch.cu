@@ -27,4 +27,16 @@ BwdLauncher find_backward(int L, int H, int multi, int tmax) {
   }
   return nullptr;
 }
+Bwd2Launcher find_backward2_l10(int multi);
+Bwd2Launcher find_backward2_l20(int multi);
+Bwd2Launcher find_backward2_l64(int multi);
+Bwd2Launcher find_backward2(int L, int H, int multi) {
+  if (H != 10) return nullptr;
+  switch (L) {
+    case 10: return find_backward2_l10(multi);
+    case 20: return find_backward2_l20(multi);
+    case 64: return find_backward2_l64(multi);
+  }
+  return nullptr;
+}
 }  // namespace gns

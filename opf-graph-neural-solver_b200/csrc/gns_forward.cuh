@@ -18,11 +18,13 @@ namespace gns {
 #define GNS_GRAD_MREG 1   // training variant: keep the latent in registers too
 #endif
 
-// GRADV: 0 = inference, 1 = training with grid-major activation rows, 2 = training with interleaved rows (ActLayout)
+// GRADV: 0 = inference, 1 = training with grid-major activation rows, 2 = training with interleaved rows (ActLayout),
+//        3 = training with the per-grid block checkpoints of the warp-specialised backward kernel (Act2Layout)
 template <int L, int H, bool MULTI, int VG, int TMAX, int GRADV>
 __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   constexpr bool GRAD = GRADV != 0;
   constexpr bool INTER = GRADV == 2;
+  constexpr bool V3 = GRADV == 3;
   constexpr WLayout W = make_wlayout(L, H, MULTI);
   constexpr int HP = pad4(H);
   constexpr int PO = MULTI ? L : 1;
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const uint16_t* const t_rank = s_topo + a.to.rank_of;
   const uint16_t* const t_prim = s_topo + a.to.prim_of;
   const uint16_t* const t_gsz = s_topo + a.to.gsz;
+  const uint16_t* const t_brank = s_topo + a.to.brank;
   __syncthreads();
   // slot bookkeeping (constant over batches)
   const int sl = slot_on ? slot : 0;
@@ -131,6 +134,29 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     }
     __syncthreads();
   }
+
+  // GRADV = 3: state checkpoint `kidx` of the thread's own bus (rows indexed by bus rank, one block per grid) and
+  // zeros in the padding columns; the values were written by this thread, so no barrier is needed in front
+  const int my_brank = (V3 && slot_on) ? (int)t_brank[sl] : 0;
+  auto ckpt2_store = [&](long long g0, int kidx) {
+    const int NbP = a.a2.NbP;
+    if (bus_on) {
+#pragma unroll 4
+      for (int r = 0; r < 4 + L; ++r) {
+        float x[VG];
+        IO::ld(x, s_state + r * NG + slot * G + gcol);
+#pragma unroll
+        for (int g = 0; g < VG; ++g)
+          __stcs(a.ck2 + ((size_t)(g0 + gcol + g) * (K + 1) + kidx) * (size_t)a.a2.state + r * NbP + my_brank, x[g]);
+      }
+    }
+    const int npad = NbP - N;
+    for (int i = tid; i < npad * (4 + L) * G; i += T) {
+      const int gl = i / (npad * (4 + L)), rem = i - gl * (npad * (4 + L));
+      const int r = rem / npad, c = N + rem - r * npad;
+      __stcs(a.ck2 + ((size_t)(g0 + gl) * (K + 1) + kidx) * (size_t)a.a2.state + r * NbP + c, 0.f);
+    }
+  };
 
   for (int batch = blockIdx.x; batch < a.nbatch; batch += gridDim.x) {
     const long long g0 = (long long)batch * G;
@@ -256,7 +282,28 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         for (int i = tid; i < W.wstep / 4; i += T) dst[i] = __ldg(src + i);
       }
       // ---------------- checkpoint: state entering step k (k >= 1) ----------------
-      if (GRAD && k >= 1) {
+      if constexpr (V3) {
+        ckpt2_store(g0, k);
+        // zeros in the padding columns of this step's activation blocks
+        const int pb = a.a2.NbP - N, pl = a.a2.EP - E;
+        const int nb = 9 * H * pb, nl = (MULTI ? 3 : 1) * H * pl;
+        for (int i = tid; i < (nb + nl) * G; i += T) {
+          const int gl = i / (nb + nl);
+          int rem = i - gl * (nb + nl);
+          float* base = a.act + ((size_t)(g0 + gl) * K + k) * (size_t)a.a2.step;
+          if (rem < nb) {
+            const int blk = rem / (H * pb); rem -= blk * (H * pb);       // blk = 3 q + {h2L, h1L, A}
+            const int r = rem / pb, c = N + rem - r * pb;
+            const int q = blk / 3, w = blk - 3 * q;
+            __stcs(base + (w == 0 ? a.a2.h2L[q] : (w == 1 ? a.a2.h1L[q] : a.a2.A[q])) + r * a.a2.NbP + c, 0.f);
+          } else {
+            rem -= nb;
+            const int q = rem / (H * pl); rem -= q * (H * pl);
+            const int r = rem / pl, c = E + rem - r * pl;
+            __stcs(base + a.a2.h1line[q] + r * a.a2.EP + c, 0.f);
+          }
+        }
+      } else if (GRAD && k >= 1) {
         const int nst4 = (4 + L) * NG / 4;
         float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (k - 1)) * (size_t)((4 + L) * NG));
         const float4* srcs = reinterpret_cast<const float4*>(s_state);
@@ -275,7 +322,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       {
         const int n = pslot;                         // the bus's state lives in its primary slot
         // training: hidden activations of this step for the backward kernel (see ActLayout)
-        float* const act_k = GRAD ? a.act + ((size_t)batch * K + k) * (size_t)a.al.total : nullptr;
+        float* const act_k = !GRAD ? nullptr
+                             : (V3 ? a.act + ((size_t)(g0 + gcol) * K + k) * (size_t)a.a2.step
+                                   : a.act + ((size_t)batch * K + k) * (size_t)a.al.total);
+        const int gstr2 = V3 ? K * a.a2.step : 0;          // floats between the blocks of consecutive grids (GRADV = 3)
         float* st = s_state + n * G + gcol;
         const float* sm_m = st + 4 * NG;
         const float degf = (float)(e_full1 - e_in0); // in-degree of the bus (primary)
@@ -350,7 +400,19 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
               for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(z2, z[j], wphi + W.phi_w2 + j * HP);
 #pragma unroll
               for (int o = 0; o < H; ++o) { lrelu_vec<VG>(z2[o]); add_vec<VG>(A[o], z2[o]); }
-              if constexpr (GRAD) {
+              if constexpr (V3) {
+                // h1 rows of the phi net (column in_pos) and the slope bits of (h1, h2) of this slot's (e - e_in0)-th line
+                const int ep = a.a2.EP + opaque_zero();
+                stg_rows<H, VG, false>(act_k + a.a2.h1line[MULTI ? q : 0] + (int)t_inp[e], ep, gstr2, z);
+                uint32_t wb[VG];
+#pragma unroll
+                for (int g = 0; g < VG; ++g) wb[g] = 0u;
+                slope_bits<H, VG>(wb, z, 0);
+                slope_bits<H, VG>(wb, z2, H);
+                uint32_t* mp = reinterpret_cast<uint32_t*>(act_k + a.a2.mask[MULTI ? q : 0]) + (1 + e - e_in0) * a.a2.NsM + sl;
+#pragma unroll
+                for (int g = 0; g < VG; ++g) __stcs(mp + (size_t)g * gstr2, wb[g]);
+              } else if constexpr (GRAD) {
                 // (the opaque zero keeps the 2H row offsets from being hoisted out of the line loop into spills)
                 const int rl = a.al.rl + opaque_zero();
                 float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.gl + (int)t_inp[e] * a.al.ls;
@@ -373,8 +435,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             }
           }
           if (!prim) continue;
-          float* const ab = GRAD ? act_k + (size_t)(q * 3 * H) * a.al.rb + gcol * a.al.gs + n * a.al.is : nullptr;
-          if constexpr (GRAD) {
+          float* const ab = (GRAD && !V3) ? act_k + (size_t)(q * 3 * H) * a.al.rb + gcol * a.al.gs + n * a.al.is : nullptr;
+          if constexpr (V3) {
+            stg_rows<H, VG, false>(act_k + a.a2.A[q] + my_brank, a.a2.NbP, gstr2, A);
+          } else if constexpr (GRAD) {
             stg_rows<H, VG, INTER>(ab, a.al.rb, a.al.gs, A);
           }
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
@@ -425,7 +489,18 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
           for (int j = 0; j < H; ++j) row_axpy<H, HP, VG>(z2, zL[j], wln + W.ln_w2 + j * HP);
 #pragma unroll
           for (int o = 0; o < H; ++o) lrelu_vec<VG>(z2[o]);
-          if constexpr (GRAD) {
+          if constexpr (V3) {
+            stg_rows<H, VG, false>(act_k + a.a2.h1L[q] + my_brank, a.a2.NbP, gstr2, zL);
+            stg_rows<H, VG, false>(act_k + a.a2.h2L[q] + my_brank, a.a2.NbP, gstr2, z2);
+            uint32_t wb[VG];
+#pragma unroll
+            for (int g = 0; g < VG; ++g) wb[g] = 0u;
+            slope_bits<H, VG>(wb, zL, 0);
+            slope_bits<H, VG>(wb, z2, H);
+            uint32_t* mp = reinterpret_cast<uint32_t*>(act_k + a.a2.mask[q]) + sl;
+#pragma unroll
+            for (int g = 0; g < VG; ++g) __stcs(mp + (size_t)g * gstr2, wb[g]);
+          } else if constexpr (GRAD) {
             stg_rows<H, VG, INTER>(ab + H * a.al.rb, a.al.rb, a.al.gs, zL);
             stg_rows<H, VG, INTER>(ab + 2 * H * a.al.rb, a.al.rb, a.al.gs, z2);
           }
@@ -565,7 +640,12 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         lam[g] = (pglob < sPset[g]) ? l1 : l2;
         lo_arm[g] = lam[g] < 0.5f;
       }
-      if (GRAD && tid < NGQ) IO::st(a.pglob + ((size_t)batch * K + k) * G + gcol, pj);
+      if constexpr (V3) {
+        if (tid < NGQ) {
+#pragma unroll
+          for (int g = 0; g < VG; ++g) a.pglob[(size_t)(g0 + gcol + g) * K + k] = pj[g];
+        }
+      } else if (GRAD && tid < NGQ) IO::st(a.pglob + ((size_t)batch * K + k) * G + gcol, pj);
       if (bus_on) {
         const int n = slot;
         float pgs[VG];
@@ -626,7 +706,9 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     }  // k
 
     // ---------------- outputs ----------------
-    if (GRAD) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
+    if constexpr (V3) {
+      ckpt2_store(g0, K);
+    } else if (GRAD) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
       const int nst4 = (4 + L) * NG / 4;
       float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)((4 + L) * NG));
       const float4* srcs = reinterpret_cast<const float4*>(s_state);

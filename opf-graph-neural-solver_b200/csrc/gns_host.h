@@ -15,6 +15,7 @@ struct gns_plan {
   int N = 0, E = 0, Gn = 0;
   int Ns = 0;                       // bus slots (high-degree buses own 2 or 4)
   int deg_cap = 2, max_gsz = 1;
+  int max_walk = 0;                 // most in-lines walked by one slot
   int num_sms = 0;
   int smem_optin = 0;
   // host copies (int32) for export and tests
@@ -47,6 +48,17 @@ struct Geometry {
 
 struct ModelDims { int K, L, H, multi; };
 
+// launch geometry of the warp-specialised backward kernel (gns_backward2.cuh): one grid per CTA at a time
+struct Bwd2Geom {
+  bool ok = false;
+  int PW = 0, CW = 0, T = 0, ctas = 0;
+  size_t smem_bytes = 0;
+  Act2Layout a2{};
+};
+// eligible iff the grid is large enough to fill the producer warps, the blocks fit shared memory and kernels are
+// built for the dims; GNS_BWD2=0 / 1 forces the first / this kernel (A/B measurements, tests)
+Bwd2Geom choose_bwd2(const gns_plan* plan, const ModelDims& md, long long S);
+
 void set_error(const std::string& msg);
 
 // workspace carving (all offsets in bytes, 256-byte aligned)
@@ -67,7 +79,7 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
 // GNS_ACT_LAYOUT=grid / interleaved overrides (A/B measurements)
 bool act_grid_major(const Geometry& bwd);
 Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S, bool need_grad,
-                         const Geometry& fwd, const Geometry& bwd);
+                         const Geometry& fwd, const Geometry& bwd, const Bwd2Geom& b2);
 
 // canonical <-> packed parameter maps
 int64_t canonical_param_count(const ModelDims& md);
@@ -80,5 +92,8 @@ FwdLauncher find_forward(int L, int H, int multi, int VG, int tmax);
 struct BwdArgs;
 typedef cudaError_t (*BwdLauncher)(const BwdArgs& a, const Geometry& g, cudaStream_t st);
 BwdLauncher find_backward(int L, int H, int multi, int tmax);
+struct Bwd2Args;
+typedef cudaError_t (*Bwd2Launcher)(const Bwd2Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st);
+Bwd2Launcher find_backward2(int L, int H, int multi);
 
 }  // namespace gns

@@ -3,6 +3,7 @@
 #pragma once
 #include "gns_forward.cuh"
 #include "gns_backward.cuh"
+#include "gns_backward2.cuh"
 #include "gns_host.h"
 
 namespace gns {
@@ -25,6 +26,10 @@ static cudaError_t launch_forward_g(const FwdArgs& a, const Geometry& g, cudaStr
 template <int L, int H, bool MULTI, int VG, int TMAX>
 static cudaError_t launch_forward(const FwdArgs& a, const Geometry& g, cudaStream_t st) {
   if (!a.need_grad) return launch_forward_g<L, H, MULTI, VG, TMAX, 0>(a, g, st);
+  if (a.need_grad == 2) {
+    if constexpr (L <= 20 && TMAX != 1024) return launch_forward_g<L, H, MULTI, VG, TMAX, 3>(a, g, st);
+    else return cudaErrorInvalidValue;
+  }
   return a.al.gs == 1 ? launch_forward_g<L, H, MULTI, VG, TMAX, 2>(a, g, st)
                       : launch_forward_g<L, H, MULTI, VG, TMAX, 1>(a, g, st);
 }
@@ -57,6 +62,26 @@ static cudaError_t launch_backward(const BwdArgs& a, const Geometry& g, cudaStre
   const int ctas = std::min(std::min(g.nbatch, occ * g.num_sms), g.ctas);
   kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int L, int H, bool MULTI>
+static cudaError_t launch_backward2(const Bwd2Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st) {
+  auto kern = gns_backward2_kernel<L, H, MULTI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, g.T, g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  // g.ctas x CW accumulator blocks were provisioned by the host; never launch more CTAs than that
+  const int ctas = (int)std::min<long long>(std::min<long long>(a.S, (long long)occ * num_sms), g.ctas);
+  kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
+  return cudaGetLastError();
+}
+template <int L, int H>
+static Bwd2Launcher pick_backward2(int multi) {
+  if constexpr (L <= 20) return multi ? launch_backward2<L, H, true> : launch_backward2<L, H, false>;
+  else return nullptr;
 }
 
 template <int L, int H>

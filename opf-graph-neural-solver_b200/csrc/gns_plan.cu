@@ -79,6 +79,8 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
 
 // extra shared memory of the backward kernel, in floats (see gns_backward.cuh)
 int backward_extra_floats(int N, int E, int G, int L, int H, int T);
+// shared memory of the warp-specialised backward kernel, in floats (see gns_backward2.cuh)
+int make_bwd2_smem_floats(int L, int H, int E, int wstep, const Act2Layout& a2);
 
 // Warp w runs on SM sub-partition w % 4.  A warp's bus phase costs ~ (1 + c * max lines walked by
 // a lane of its bus group), c ~ 0.2 forward / 0.3 backward (instruction counts).  Groups are placed
@@ -192,6 +194,31 @@ bool choose_geometry(const gns_plan* plan, const ModelDims& md, long long S, boo
   return true;
 }
 
+int bwd2_threads_limit() { return 384; }
+
+Bwd2Geom choose_bwd2(const gns_plan* plan, const ModelDims& md, long long S) {
+  Bwd2Geom g{};
+  const int force = env_int("GNS_BWD2", -1);
+  if (force == 0 || S <= 0) return g;
+  if (md.H != 10 || (md.L != 10 && md.L != 20)) return g;           // instantiated dims (latent in registers: L <= 20)
+  if (plan->max_walk > 4 || plan->max_walk < 1) return g;            // kB2MaxWalk
+  const int min_slots = env_int("GNS_BWD2_MIN_SLOTS", 96);
+  if (force != 1 && plan->Ns < min_slots) return g;                   // small grids: several grids per CTA (first kernel)
+  const int PW = ((plan->Ns + 1) / 2 + 31) / 32;
+  const int CW = std::max(1, env_int("GNS_BWD2_CW", PW));
+  if (PW > 8 || CW > 8 || (PW + CW) * 32 > bwd2_threads_limit()) return g;
+  g.a2 = make_act2_layout(md.L, md.H, plan->N, plan->Ns, plan->E, plan->max_walk);
+  if (md.L * g.a2.NbP > 2 * md.H * g.a2.EP) return g;                // the adj m' rows live in the two line blocks
+  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
+  const size_t bytes = (size_t)make_bwd2_smem_floats(md.L, md.H, plan->E, W.wstep, g.a2) * 4;
+  if ((int)bytes > plan->smem_optin) return g;
+  g.PW = PW; g.CW = CW; g.T = (PW + CW) * 32; g.smem_bytes = bytes;
+  const int per_sm = std::max(1, std::min((int)((size_t)233472 / (bytes + 1024)), 65536 / (g.T * 168)));
+  g.ctas = (int)std::min<long long>(S, (long long)plan->num_sms * per_sm);
+  g.ok = true;
+  return g;
+}
+
 bool act_grid_major(const Geometry& bwd) {
   if (const char* e = std::getenv("GNS_ACT_LAYOUT")) {
     if (e[0] == 'g') return true;
@@ -272,13 +299,24 @@ const gns_plan::PackMap* get_pack_map(gns_plan* plan, const ModelDims& md) {
 }
 
 Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S, bool need_grad,
-                         const Geometry& fwd, const Geometry& bwd) {
+                         const Geometry& fwd, const Geometry& bwd, const Bwd2Geom& b2) {
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   Workspace w{};
   size_t o = 0;
   w.packed_params = o; o = align(o + (size_t)md.K * W.wstep * 4);
-  if (need_grad) {
+  if (need_grad && b2.ok) {
+    // per-grid block checkpoints of the warp-specialised backward kernel (Act2Layout); the forward writes whole
+    // CTA-batches, so the grid count is rounded up to its batch size
+    const size_t Sg = (size_t)fwd.nbatch * fwd.G;
+    const FragLayout FL = make_frag_layout(md.L, md.H);
+    w.ckpt = o; o = align(o + Sg * (md.K + 1) * (size_t)b2.a2.state * 4);
+    w.pglob = o; o = align(o + Sg * md.K * 4);
+    w.act = o; o = align(o + Sg * md.K * (size_t)b2.a2.step * 4);
+    w.gpartial = o; o = align(o + (size_t)b2.ctas * b2.CW * md.K * FL.step * 4);   // one block per consumer warp
+    w.fragsum = o; o = align(o + (size_t)md.K * FL.step * 4);
+    w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
+  } else if (need_grad) {
     const size_t nst = (size_t)(4 + md.L) * row_stride(plan->Ns * fwd.G);
     w.ckpt = o; o = align(o + (size_t)fwd.nbatch * md.K * nst * 4);
     w.pglob = o; o = align(o + (size_t)fwd.nbatch * md.K * fwd.G * 4);
@@ -377,7 +415,7 @@ extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* 
 
   // device index block in slot numbering
   p->to = make_topo_offsets(n_bus, Ns, n_line, n_gen);
-  std::vector<uint16_t> blk(p->to.total, 0);
+  std::vector<uint16_t> blk(p->to.total_ext, 0);
   for (int e = 0; e < n_line; ++e) {
     blk[p->to.fi + e] = (uint16_t)prim_slot_of_bus[f_bus[e]];
     blk[p->to.ti + e] = (uint16_t)prim_slot_of_bus[t_bus[e]];
@@ -414,8 +452,15 @@ extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* 
       blk[p->to.ext_of + s] = (uint16_t)p->slot_bus[s];
       blk[p->to.prim_of + s] = (uint16_t)p->slot_primary[s];
       blk[p->to.gsz + s] = (uint16_t)p->slot_gsz[s];
+      blk[p->to.brank + s] = (uint16_t)p->bus_rank[p->slot_bus[s]];
+      p->max_walk = std::max(p->max_walk, p->slot_in_end[s] - p->slot_in_begin[s]);
       // non-primary slots keep empty out / generator ranges (zero-initialised begin == end)
     }
+    for (int e = 0; e < n_line; ++e) {
+      blk[p->to.fr + e] = (uint16_t)p->bus_rank[f_bus[e]];
+      blk[p->to.tr + e] = (uint16_t)p->bus_rank[t_bus[e]];
+    }
+    for (int r = 0; r < n_bus; ++r) blk[p->to.ext_rank + r] = (uint16_t)p->bus_order[r];
   }
   std::vector<float> expect(2 * n_line + n_gen);
   for (int e = 0; e < n_line; ++e) { expect[e] = (float)(f_bus[e] + 1); expect[n_line + e] = (float)(t_bus[e] + 1); }

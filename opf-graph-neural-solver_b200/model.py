@@ -151,6 +151,17 @@ class GNS(nn.Module):
         self.hidden_dim = hidden_dim
         self.gamma = gamma
         self.K = K
+        # Kernels are instantiated for hidden_dim 10 and latent_dim 10 / 20 / 64 and K <= 64 (every value the
+        # reference's own scripts use); fail here rather than at the first forward.  (Skipped when the library
+        # has not been built yet: constructing / loading checkpoints needs no kernel.)
+        try:
+            lib = _lib.load_library()
+        except RuntimeError:
+            lib = None
+        if lib is not None and (not lib.gns_dims_supported(int(latent_dim), int(hidden_dim)) or not 1 <= K <= 64):
+            raise ValueError(f"GNS (B200 build): no sm_100a kernel for latent_dim={latent_dim}, hidden_dim={hidden_dim}, "
+                             f"K={K}; built: hidden_dim=10, latent_dim in (10, 20, 64), 1 <= K <= 64. There is no "
+                             "fallback path.")
         # --- not part of the reference surface ---
         self.validate_topology = True     # device-side check that a batch shares the plan's topology
         self._flat = None                 # flat float32 parameter storage, state_dict order
@@ -163,8 +174,10 @@ class GNS(nn.Module):
         # graph instead (needed for per-parameter hooks, torch.autograd.grad w.r.t. parameters, DDP).
         self.per_parameter_autograd = False
         self._flat_leaf = None
+        self._leaf_owner = None           # id() of the module that registered the leaf's hook (copies lose hooks)
         self._grad_flat = None
         self._grad_aliases = None
+        self._topo_ok_key = None          # (ptr, version, shape) of the last device tensors that passed the topology check
         self._plans = {}                  # topology key -> TopologyPlan
         self._last_plan = None
 
@@ -208,10 +221,13 @@ class GNS(nn.Module):
 
     def _leaf(self) -> torch.Tensor:
         """The flat buffer as the single autograd leaf of the fast gradient path."""
-        if self._flat_leaf is None:
+        # copy.deepcopy / pickling copy the cached leaf WITHOUT its hook (and the gradient aliases without their
+        # owner): a copy therefore rebuilds them on first use instead of silently training nothing
+        if self._flat_leaf is None or self._leaf_owner != id(self):
             leaf = self._flat.detach().requires_grad_(True)      # shares storage with the parameters
             leaf.register_post_accumulate_grad_hook(self._deliver_gradients)
-            self._flat_leaf = leaf
+            self._flat_leaf, self._leaf_owner = leaf, id(self)
+            self._grad_flat = self._grad_aliases = None
         return self._flat_leaf
 
     def _deliver_gradients(self, leaf):
@@ -233,22 +249,46 @@ class GNS(nn.Module):
             self._grad_flat.copy_(g)
         else:
             self._grad_flat.add_(g)
-        for (p, _), alias in zip(params, self._grad_aliases):
-            if p.requires_grad and p.grad is None:
-                p.grad = alias
+        off = 0
+        for (p, n), alias in zip(params, self._grad_aliases):
+            if p.requires_grad:
+                if p.grad is None:
+                    p.grad = alias
+                elif p.grad.data_ptr() != alias.data_ptr():
+                    # a foreign gradient tensor (set by the user, or moved by Module.to()): accumulate into it
+                    p.grad.add_(g[off:off + n].view(p.shape).to(p.grad.device))
+            off += n
         self._last_grad_flat = self._grad_flat
 
     # ------------------------------------------------------------------ topology plans
-    def plan_for(self, lines: torch.Tensor, generators: torch.Tensor, n_bus: int) -> TopologyPlan:
+    def plan_for(self, lines: torch.Tensor, generators: torch.Tensor, n_bus: int, host=None) -> TopologyPlan:
+        """Plan of the batch's topology.  With ``validate_topology`` every grid of the batch is checked against it:
+        on the host when the caller's tensors live there (``host`` = the caller's (lines, generators); reference-style
+        per-sample loops then never synchronise the stream), else by one small kernel + flag read, skipped when the
+        same device tensors (address, version, shape) already passed."""
         dev_index = lines.device.index if lines.device.index is not None else torch.cuda.current_device()
+
+        def ok(plan):
+            if not self.validate_topology:
+                return True
+            if host is not None:
+                return plan.matches_host(*host)
+            key = (lines.data_ptr(), lines._version, tuple(lines.shape), generators.data_ptr(), generators._version, id(plan))
+            if key == self._topo_ok_key:
+                return True
+            if plan.matches(lines, generators):
+                self._topo_ok_key = key
+                return True
+            return False
+
         plan = self._last_plan
         if plan is not None and plan.device == dev_index and \
                 (plan.n_bus, plan.n_line, plan.n_gen) == (n_bus, lines.shape[1], generators.shape[1]):
-            if not self.validate_topology or plan.matches(lines, generators):
+            if ok(plan):
                 return plan
         plan = TopologyPlan.from_tensors(lines, generators, n_bus, dev_index)
         plan = self._plans.setdefault((dev_index,) + plan.key(), plan)
-        if self.validate_topology and not plan.matches(lines, generators):
+        if not ok(plan):
             raise ValueError("all grids of a batch must share one topology (f_bus, t_bus, generator buses)")
         self._last_plan = plan
         return plan
@@ -285,6 +325,7 @@ class GNS(nn.Module):
             h2d.wait_event(start)
             flat = self.flat_parameters()
             plan = None
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)     # set by the per-chunk topology checks
             for i, a in enumerate(range(0, S, chunk)):
                 b = min(S, a + chunk)
                 slot = i % 2
@@ -298,6 +339,8 @@ class GNS(nn.Module):
                 d = [t[:b - a] for t in dbuf[slot]]
                 if plan is None:
                     plan = self.plan_for(d[1], d[2], N)
+                elif self.validate_topology:
+                    plan.check_async(d[1], d[2], bad)           # every chunk, without stalling the pipeline
                 res = _run_forward(self, plan, False, d[0], d[1], d[2], flat)[:4]
                 free[slot].record(comp)
                 done = torch.cuda.Event(); done.record(comp)
@@ -308,6 +351,8 @@ class GNS(nn.Module):
                         dst[a:b].copy_(src, non_blocking=True)
                 keep.append(res)
             d2h.synchronize()
+            if self.validate_topology and int(bad.item()):
+                raise ValueError("all grids of a batch must share one topology (f_bus, t_bus, generator buses)")
         return out
 
     # ------------------------------------------------------------------ forward
@@ -338,7 +383,8 @@ class GNS(nn.Module):
         buses_d, lines_d, gens_d = prep(buses), prep(lines), prep(generators)
         with torch.cuda.device(dev):
             flat = self.flat_parameters()
-            plan = self.plan_for(lines_d, gens_d, buses_d.shape[1])
+            host = (lines, generators) if (in_dev.type == "cpu" and lines.dtype == torch.float32) else None
+            plan = self.plan_for(lines_d, gens_d, buses_d.shape[1], host=host)
             params = [p for p, _ in self._param_list]
             need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
             if need_grad and not self.per_parameter_autograd:

@@ -70,6 +70,22 @@ class TopologyPlan:
             raise RuntimeError(_lib.last_error())
         return rc == 0
 
+    def matches_host(self, lines: torch.Tensor, generators: torch.Tensor) -> bool:
+        """Same check on HOST tensors (reference-style CPU inputs): no device work, no stream synchronisation."""
+        if getattr(self, "_expect_host", None) is None:
+            self._expect_host = (torch.from_numpy(self.f_bus.astype(np.float32) + 1), torch.from_numpy(self.t_bus.astype(np.float32) + 1),
+                                 torch.from_numpy(self.gen_bus.astype(np.float32) + 1))
+        ef, et, eg = self._expect_host
+        l, g = lines.detach(), generators.detach()
+        return bool((l[..., 0] == ef).all()) and bool((l[..., 1] == et).all()) and bool((g[..., 0] == eg).all())
+
+    def check_async(self, lines: torch.Tensor, generators: torch.Tensor, flag: torch.Tensor):
+        """Device-side check without synchronisation: ORs 1 into the int32 device tensor `flag` on a mismatch."""
+        rc = self._lib.gns_check_topology_async(self._h, lines.data_ptr(), generators.data_ptr(), lines.shape[0],
+                                                flag.data_ptr(), torch.cuda.current_stream(lines.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(_lib.last_error())
+
     def launch_info(self, S, K, latent_dim, hidden_dim, multiple_phi, backward=False):
         out = (C.c_int32 * 8)()
         rc = self._lib.gns_launch_info(self._h, S, K, latent_dim, hidden_dim, int(multiple_phi),

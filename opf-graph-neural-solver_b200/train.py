@@ -27,16 +27,30 @@ class FlatAdam:
         lib = _lib.load_library()
         flat = self.model.flat_parameters()
         params = list(self.model.parameters())
-        grad = flat_gradient(params)
-        if grad is None:   # gradients did not come from GNS.backward as one buffer
-            grad = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
         if self.exp_avg is None or self.exp_avg.device != flat.device:
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+        # The alias of all parameter gradients is only usable when it covers EVERY parameter in order: with frozen
+        # parameters (grad None) it is shorter or starts at an offset, and the kernel would pair gradients with
+        # the wrong parameters.
+        grad = flat_gradient(params)
+        frozen = None
+        if grad is None or grad.numel() != flat.numel():
+            grad = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
+                              for p in params])
+            # torch.optim.Adam skips parameters without a gradient (no moment update, no step): restore them after
+            off, frozen = 0, []
+            for p in params:
+                if p.grad is None:
+                    sl = slice(off, off + p.numel())
+                    frozen.append((sl, flat[sl].clone(), self.exp_avg[sl].clone(), self.exp_avg_sq[sl].clone()))
+                off += p.numel()
         self.step_count += 1
         rc = lib.gns_adam_step(flat.data_ptr(), grad.contiguous().data_ptr(), self.exp_avg.data_ptr(),
                                self.exp_avg_sq.data_ptr(), flat.numel(), self.lr, self.betas[0], self.betas[1],
                                self.eps, self.step_count, torch.cuda.current_stream(flat.device).cuda_stream)
         _lib.check(rc, "gns_adam_step")
+        for sl, pv, m1, m2 in frozen or ():
+            flat[sl].copy_(pv); self.exp_avg[sl].copy_(m1); self.exp_avg_sq[sl].copy_(m2)
 
 
 def checkpoint_name(case_nr, model, optimizer_name="Adam"):
