@@ -107,6 +107,17 @@ int gns_check_topology(const gns_plan* plan, const float* lines, const float* ge
 int gns_check_topology_async(const gns_plan* plan, const float* lines, const float* gens,
                              int64_t S, int* flag, void* stream);
 
+/* Compact input format -> the reference's packed rows, on the device (replaces the host-side row build of
+ * ref GNS/utils.py:17-41 for batches of ONE case).  Between samples only Pd,Qd | r,x,b,tau,shift | vg,Pg vary
+ * (ref GNS/augment_grids.py:35-53); the rest is constant per case and Pg_set is a copy of Pg (ref GNS/utils.py:38).
+ *   bus_var [S][n_bus][2] = Pd,Qd      line_var [S][n_line][5] = r,x,b,tau,shift    gen_var [S][n_gen][2] = vg,Pg
+ *   bus_const [n_bus][4] = bus_i,type,Gs,Bs   line_const [n_line][2] = f_bus,t_bus  gen_const [n_gen][4] = bus_i,Pmax,Pmin,qg
+ * writes buses [S][n_bus][6], lines [S][n_line][7], gens [S][n_gen][7] (all device pointers). */
+int gns_expand_inputs(const float* bus_var, const float* line_var, const float* gen_var,
+                      const float* bus_const, const float* line_const, const float* gen_const,
+                      int64_t S, int n_bus, int n_line, int n_gen,
+                      float* buses, float* lines, float* gens, void* stream);
+
 /* Layout maps of the gradient path, for tests and tools (host only, no GPU needed).
  *   "pack": canonical (state_dict order, all K steps) index -> packed index        [gns_param_count]
  *   "frag": packed index inside ONE step's block -> index inside that step's fragment-order

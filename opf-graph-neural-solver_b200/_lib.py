@@ -11,7 +11,7 @@ _LIB = None
 SYMBOLS = [
     "gns_plan_create", "gns_plan_destroy", "gns_plan_export", "gns_dims_supported",
     "gns_param_count", "gns_workspace_bytes", "gns_forward", "gns_backward",
-    "gns_check_topology", "gns_check_topology_async", "gns_launch_info", "gns_layout_export", "gns_adam_step", "gns_measure_ffma_flops", "gns_measure_ffma2_flops",
+    "gns_check_topology", "gns_check_topology_async", "gns_expand_inputs", "gns_launch_info", "gns_layout_export", "gns_adam_step", "gns_measure_ffma_flops", "gns_measure_ffma2_flops",
     "gns_last_error", "gns_version",
 ]
 
@@ -65,6 +65,8 @@ def load_library():
     lib.gns_check_topology.restype = i32
     lib.gns_check_topology_async.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.gns_check_topology_async.restype = i32
+    lib.gns_expand_inputs.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]
+    lib.gns_expand_inputs.restype = i32
     lib.gns_launch_info.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp]
     lib.gns_launch_info.restype = i32
     lib.gns_layout_export.argtypes = [C.c_char_p, i32, i32, i32, i32, vp, i32]

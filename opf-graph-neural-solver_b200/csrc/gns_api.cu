@@ -65,6 +65,39 @@ __global__ void check_topology_kernel(const float* __restrict__ lines, const flo
   if (bad) atomicOr(flag, 1);
 }
 
+// Compact input format -> the reference's packed rows (ref GNS/utils.py:17-41).  Between the samples of one case only
+// Pd, Qd | r, x, b, tau, shift | vg, Pg vary (ref GNS/augment_grids.py:35-53); bus_i, type, Gs, Bs | f_bus, t_bus |
+// bus_i, Pmax, Pmin, qg are constants of the case and Pg_set is a copy of Pg (ref GNS/utils.py:38), so a host batch
+// ships 2N + 5E + 2Gn floats per grid instead of 6N + 7E + 7Gn.  One thread per output row.
+__global__ void expand_inputs_kernel(const float* __restrict__ bv, const float* __restrict__ lv, const float* __restrict__ gv,
+                                     const float* __restrict__ cb, const float* __restrict__ cl, const float* __restrict__ cg,
+                                     long long S, int N, int E, int Gn, float* __restrict__ buses, float* __restrict__ lines,
+                                     float* __restrict__ gens) {
+  const long long per = (long long)N + E + Gn, total = S * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / per;
+    int r = (int)(i - s * per);
+    if (r < N) {
+      const float* v = bv + (s * N + r) * 2;
+      const float* c = cb + r * 4;
+      float* o = buses + (s * N + r) * 6;
+      o[0] = c[0]; o[1] = c[1]; o[2] = v[0]; o[3] = v[1]; o[4] = c[2]; o[5] = c[3];
+    } else if (r < N + E) {
+      r -= N;
+      const float* v = lv + (s * E + r) * 5;
+      const float* c = cl + r * 2;
+      float* o = lines + (s * E + r) * 7;
+      o[0] = c[0]; o[1] = c[1]; o[2] = v[0]; o[3] = v[1]; o[4] = v[2]; o[5] = v[3]; o[6] = v[4];
+    } else {
+      r -= N + E;
+      const float* v = gv + (s * Gn + r) * 2;
+      const float* c = cg + r * 4;
+      float* o = gens + (s * Gn + r) * 7;
+      o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = v[1]; o[4] = v[0]; o[5] = c[3]; o[6] = v[1];
+    }
+  }
+}
+
 // torch.optim.Adam defaults (ref GNS/main.py:243): no weight decay, no amsgrad
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
@@ -278,6 +311,22 @@ extern "C" int gns_check_topology(const gns_plan* plan, const float* lines, cons
     set_error(std::string("gns_check_topology: ") + cudaGetErrorString(cudaGetLastError())); return -2;
   }
   return flag ? 1 : 0;
+}
+
+extern "C" int gns_expand_inputs(const float* bus_var, const float* line_var, const float* gen_var, const float* bus_const,
+                                 const float* line_const, const float* gen_const, int64_t S, int n_bus, int n_line, int n_gen,
+                                 float* buses, float* lines, float* gens, void* stream) {
+  if (!bus_var || !line_var || !bus_const || !line_const || !buses || !lines || S <= 0 || n_bus <= 0 || n_line <= 0 ||
+      n_gen < 0 || (n_gen > 0 && (!gen_var || !gen_const || !gens))) {
+    set_error("gns_expand_inputs: bad arguments"); return -1;
+  }
+  const long long total = S * ((long long)n_bus + n_line + n_gen);
+  const int th = 256;
+  const int bl = (int)std::min<long long>((total + th - 1) / th, 148 * 16);
+  expand_inputs_kernel<<<bl, th, 0, (cudaStream_t)stream>>>(bus_var, line_var, gen_var, bus_const, line_const, gen_const, S, n_bus,
+                                                          n_line, n_gen, buses, lines, gens);
+  if (cudaGetLastError() != cudaSuccess) { set_error("gns_expand_inputs: launch failed"); return -2; }
+  return 0;
 }
 
 extern "C" int gns_check_topology_async(const gns_plan* plan, const float* lines, const float* gens, int64_t S, int* flag,

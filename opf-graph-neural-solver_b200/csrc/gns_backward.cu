@@ -37,7 +37,8 @@ std::vector<int32_t> build_frag_map(const ModelDims& md, bool v2) {
   const int L = md.L, H = md.H;
   const bool multi = md.multi != 0;
   const WLayout W = make_wlayout(L, H, multi);
-  const FragLayout F = make_frag_layout(L, H);
+  const FragLayout F = make_frag_layout(L, H, v2 ? kFragTile2 : kFragTile);
+  auto frag_index = [&](int r, int c) { return v2 ? gns::frag2_index(r, c) : gns::frag_index(r, c); };
   std::vector<int32_t> inv(W.wstep, -1);
   auto put = [&](int packed, int frag) { inv[packed] = frag; };
   for (int q = 0; q < 3; ++q) {
@@ -177,11 +178,12 @@ __global__ void unpack_grads_kernel(const float* __restrict__ packed, const int3
 
 // fragment-order accumulators -> state_dict-order gradient (shared by both backward kernels)
 static int fold_gradients(gns_plan* plan, const ModelDims& md, const float* gacc, int nparts, const int32_t* d_inv,
-                          const float* packed_params, char* wsb, const Workspace& ws, float* grad_params, cudaStream_t st) {
+                          const float* packed_params, char* wsb, const Workspace& ws, float* grad_params, cudaStream_t st,
+                          int tile = kFragTile) {
   const gns_plan::PackMap* pm = get_pack_map(plan, md);
   if (!pm) return -2;
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
-  const FragLayout FL = make_frag_layout(md.L, md.H);
+  const FragLayout FL = make_frag_layout(md.L, md.H, tile);
   const size_t per_part = (size_t)md.K * FL.step;
   float* packed_grad = reinterpret_cast<float*>(wsb + ws.packed_grad);
   const int th = 256;
@@ -205,7 +207,7 @@ static int run_backward2(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2
                          const float* grad_last, const float* grad_v, const float* grad_theta, float* grad_params,
                          char* wsb, cudaStream_t st) {
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
-  const FragLayout FL = make_frag_layout(md.L, md.H);
+  const FragLayout FL = make_frag_layout(md.L, md.H, kFragTile2);
   const size_t per_part = (size_t)md.K * FL.step;
   const int32_t* d_inv = get_frag_map(plan, md, true);
   if (!d_inv) return -2;
@@ -226,13 +228,26 @@ static int run_backward2(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K;
   a.PW = b2.PW; a.CW = b2.CW; a.maxwalk = plan->max_walk;
+  {
+    // warp -> role.  Mode 0: the first PW warps produce.  Mode 1 (GNS_BWD2_ROLEMAP=1): warps of SM sub-partitions 0, 1
+    // (warp % 4 < 2) produce and those of 2, 3 consume, so the warps that share an L0 instruction cache run the same code.
+    const char* rm = std::getenv("GNS_BWD2_ROLEMAP");
+    const int mode = rm ? std::atoi(rm) : 0;
+    int np = 0, nc = 0;
+    const int nw = b2.PW + b2.CW;
+    for (int w = 0; w < nw; ++w) {
+      bool prod = w < b2.PW;
+      if (mode == 1) prod = (w % 4 < 2) ? (np < b2.PW) : (nc >= b2.CW);
+      a.role[w] = prod ? (unsigned char)(np++) : (unsigned char)(0x80 | nc++);
+    }
+  }
   a.a2 = b2.a2;
   a.sm = make_bwd2_smem(md.L, md.H, plan->E, W.wstep, b2.a2);
   a.to = plan->to;
   for (int k = 0; k < md.K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(md.K - k));
   e = launch(a, b2, plan->num_sms, st);
   if (e != cudaSuccess) { set_error(std::string("backward2 launch: ") + cudaGetErrorString(e)); return -2; }
-  return fold_gradients(plan, md, gacc, nparts, d_inv, a.params, wsb, ws, grad_params, st);
+  return fold_gradients(plan, md, gacc, nparts, d_inv, a.params, wsb, ws, grad_params, st, kFragTile2);
 }
 
 int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const float* buses, const float* lines,

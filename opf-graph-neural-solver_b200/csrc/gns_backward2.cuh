@@ -8,7 +8,7 @@
 //     second slot in place of the second grid).  LeakyReLU slopes come from the bit masks the training forward
 //     stored (no activation values are read here), the physics adjoint runs on these warps as well.  Every hidden-
 //     side vector a weight gradient needs (d2L, d1L, adjP per bus; d2, d1 per line; the output adjoints) is written
-//     once to a shared-memory block [column][item].
+//     once to a shared-memory block [item][column] (branch-free: slots without a bus write to a padding item).
 //   CONSUMER warps (the other 32 CW threads): the weight gradients  dW^T[w][o] = sum_items wide[w][item] hid[o][item]
 //     as mma.sync m16n8k8 TF32 products with the 3-term split of gns_backward.cuh, but over ALL items of the grid per
 //     call: a warp accumulates its share of the items in registers and flushes every call with ONE red.global per
@@ -63,6 +63,8 @@ struct Bwd2Smem {          // offsets in floats from the start of dynamic shared
   int hid_b;               // [3][H][NbP]   D2L, D1L, ADJP
   int hid_l;               // [2][H][EP]    D2LN, D1LN (contiguous: also hosts the adj m' rows [L][NbP])
   int act;                 // [kB2ActSlots][H][EP]
+  int zrow;                // [EP] zeros: wide row of the padding rows of a tile (loads stay unconditional)
+  int zc;                  // [2][40] hidden-side constants for MMA rows past the real columns: zeros, and (1, 0) every 10 floats
   int red;                 // [2][8][4]
   int topo;                // uint16 [7][Epad]: fa, ta, fr, tr, in_ids, in_pos, out_ids
   int mbar;                // [Bwd2Bar::COUNT] x 8 bytes
@@ -90,6 +92,8 @@ __host__ __device__ inline Bwd2Smem make_bwd2_smem(int L, int H, int E, int wste
   s.hid_b = take(3 * H * NbP);
   s.hid_l = take(2 * H * EP);
   s.act = take(kB2ActSlots * H * EP);
+  s.zrow = take(EP);
+  s.zc = take(80);
   s.red = take(2 * 8 * 4);
   s.topo = take((7 * pad4(E) + 1) / 2);
   s.mbar = take(2 * Bwd2Bar::COUNT);
@@ -109,6 +113,7 @@ struct Bwd2Args {
   long long S;
   int N, Ns, E, Gn, K;
   int PW, CW;
+  unsigned char role[32];   // warp -> producer rank (0 .. PW-1) or 0x80 | consumer rank
   int maxwalk;
   Act2Layout a2;
   Bwd2Smem sm;
@@ -129,8 +134,8 @@ __device__ __forceinline__ void apply_slope(float (&x)[H][2], const uint32_t (&w
 
 // deterministic sum over the producer warps of NV values (barrier 1); every producer thread gets the totals
 template <int NV>
-__device__ __forceinline__ void prod_sum(float (&x)[NV], float* red, int PW, int& parity) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void prod_sum(float (&x)[NV], float* red, int PW, int warp, int& parity) {
+  const int lane = threadIdx.x & 31;
   float* buf = red + parity * 32;
   parity ^= 1;
 #pragma unroll
@@ -149,71 +154,98 @@ __device__ __forceinline__ void prod_sum(float (&x)[NV], float* red, int PW, int
     for (int v = 0; v < NV; ++v) x[v] += buf[w * 4 + v];
 }
 
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {   // fire-and-forget, 16-byte aligned
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // One weight-gradient call of a consumer warp: D[hid c][wide r] += sum over this warp's share of the items, C hidden
-// columns (M, 10 or 11), R wide rows (N, 8 per tile).  hid(c) / row(r) return the shared-memory rows [item]; their
-// strides are = 16 mod 32 floats, so the 128-bit fragment loads (row g, items 4t..4t+3) are conflict-free.  One
-// 128-bit load feeds two k8 steps: k slots (t, t+4) are items (4t, 4t+1) in the first and (4t+2, 4t+3) in the second.
-template <int C, int R, class HidFn, class RowFn>
-__device__ __forceinline__ void cons_call(HidFn hid, RowFn row, int nch, int cw, int CW, float* __restrict__ gfrag) {
-  static_assert(C >= 8 && C <= 11, "hidden columns");
+// columns (10, or 11 = the H columns and a constant 1), R wide rows (N of the MMA, 8 per tile).
+//   hid:  ITEM-major block [item][10]; MMA row g is hidden column 2g and row g+8 column 2g+1, so (a0, a1) and (a2, a3)
+//         of a k8 step are two 64-bit loads (items 4t+2s and 4t+2s+1 of the chunk, s = k8 step) - no register
+//         shuffling in front of the HMMA; lanes of rows past the real columns read constants (zc) with stride 0.
+//   row(r): ROW-major [item] rows with a stride = 16 mod 32 floats; one 128-bit load (items 4t..4t+3) feeds both k8
+//         steps.  Rows past R read the zero row, so every load is unconditional.
+// The accumulators stay in registers over all chunks; one 128-bit reduction per lane and tile at the end.
+template <int C, int R, class RowFn>
+__device__ __forceinline__ void cons_call(const float* hid, RowFn row, const float* zrow, const float* zc, int nch, int cw,
+                                          int CW, float* __restrict__ gfrag) {
+  static_assert(C == 10 || C == 11, "hidden columns");
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int NT = (R + 7) / 8;
-  const float* const hp0 = hid(g);
-  const bool hi_ok = g + 8 < C;
-  const float* const hp1 = hid(hi_ok ? g + 8 : 0);
+  const int c0 = (nch * cw) / CW, c1 = (nch * (cw + 1)) / CW;
+  const bool a_ok = g < 5;
+  const int hs = a_ok ? 10 : 0;                                   // floats between consecutive items (0: constants)
+  const float* ap = a_ok ? hid + 2 * g + (c0 * 16 + 4 * t) * 10 : zc + ((C == 11 && g == 5) ? 40 : 0);
   const float* rp[NT];
-  bool rv[NT];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int r = nt * 8 + g;
-    rv[nt] = (nt * 8 + 8 <= R) || (r < R);
-    rp[nt] = row(rv[nt] ? r : 0);
+    rp[nt] = (((nt * 8 + 8 <= R) || (r < R)) ? row(r) : zrow) + c0 * 16 + 4 * t;
   }
   float accA[NT][4], accB[NT][4];      // big x big, and the two cross terms: separate chains (accuracy and latency)
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { accA[nt][j] = 0.f; accB[nt][j] = 0.f; }
-  const int c0 = (nch * cw) / CW, c1 = (nch * (cw + 1)) / CW;
 #pragma unroll 1
   for (int c = c0; c < c1; ++c) {
-    const int off = c * 16 + 4 * t;
-    const float4 alo = *reinterpret_cast<const float4*>(hp0 + off);
-    float4 ahi = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (hi_ok) ahi = *reinterpret_cast<const float4*>(hp1 + off);
     uint32_t ab[2][4], as[2][4];
-    split_tf32(alo.x, ab[0][0], as[0][0]); split_tf32(alo.y, ab[0][2], as[0][2]);
-    split_tf32(ahi.x, ab[0][1], as[0][1]); split_tf32(ahi.y, ab[0][3], as[0][3]);
-    split_tf32(alo.z, ab[1][0], as[1][0]); split_tf32(alo.w, ab[1][2], as[1][2]);
-    split_tf32(ahi.z, ab[1][1], as[1][1]); split_tf32(ahi.w, ab[1][3], as[1][3]);
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+      const float2 lo = *reinterpret_cast<const float2*>(ap + (2 * st) * 10);
+      const float2 hi = *reinterpret_cast<const float2*>(ap + (2 * st + 1) * 10);
+      // the tensor core reads the top 19 bits of a TF32 operand: the raw value IS its "big" part
+      ab[st][0] = __float_as_uint(lo.x); ab[st][1] = __float_as_uint(lo.y);
+      ab[st][2] = __float_as_uint(hi.x); ab[st][3] = __float_as_uint(hi.y);
+      as[st][0] = __float_as_uint(lo.x - __uint_as_float(ab[st][0] & 0xffffe000u));
+      as[st][1] = __float_as_uint(lo.y - __uint_as_float(ab[st][1] & 0xffffe000u));
+      as[st][2] = __float_as_uint(hi.x - __uint_as_float(ab[st][2] & 0xffffe000u));
+      as[st][3] = __float_as_uint(hi.y - __uint_as_float(ab[st][3] & 0xffffe000u));
+    }
+    ap += 16 * hs;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rv[nt]) b = *reinterpret_cast<const float4*>(rp[nt] + off);
-      uint32_t bb[2][2], bs[2][2];
-      split_tf32(b.x, bb[0][0], bs[0][0]); split_tf32(b.y, bb[0][1], bs[0][1]);
-      split_tf32(b.z, bb[1][0], bs[1][0]); split_tf32(b.w, bb[1][1], bs[1][1]);
+      const float4 b = *reinterpret_cast<const float4*>(rp[nt]);
+      rp[nt] += 16;
+      const uint32_t bb[2][2] = {{__float_as_uint(b.x), __float_as_uint(b.y)}, {__float_as_uint(b.z), __float_as_uint(b.w)}};
+      uint32_t bs[2][2];
+      bs[0][0] = __float_as_uint(b.x - __uint_as_float(bb[0][0] & 0xffffe000u));
+      bs[0][1] = __float_as_uint(b.y - __uint_as_float(bb[0][1] & 0xffffe000u));
+      bs[1][0] = __float_as_uint(b.z - __uint_as_float(bb[1][0] & 0xffffe000u));
+      bs[1][1] = __float_as_uint(b.w - __uint_as_float(bb[1][1] & 0xffffe000u));
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        mma_tf32(accB[nt], as[s], bb[s][0], bb[s][1]);
-        mma_tf32(accA[nt], ab[s], bb[s][0], bb[s][1]);
-        mma_tf32(accB[nt], ab[s], bs[s][0], bs[s][1]);
+      for (int st = 0; st < 2; ++st) {
+        mma_tf32(accB[nt], as[st], bb[st][0], bb[st][1]);
+        mma_tf32(accA[nt], ab[st], bb[st][0], bb[st][1]);
+        mma_tf32(accB[nt], ab[st], bs[st][0], bs[st][1]);
       }
     }
   }
+  if (lane < 24) {     // hidden columns 0..11
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    red_add_v2(gfrag + nt * kFragTile + lane * 2, accA[nt][0] + accB[nt][0], accA[nt][1] + accB[nt][1]);
-    if (C > 8 && lane < 4 * (C - 8))
-      red_add_v2(gfrag + nt * kFragTile + 64 + lane * 2, accA[nt][2] + accB[nt][2], accA[nt][3] + accB[nt][3]);
+    for (int nt = 0; nt < NT; ++nt)
+      red_add_v4(gfrag + nt * kFragTile2 + lane * 4, accA[nt][0] + accB[nt][0], accA[nt][1] + accB[nt][1],
+                 accA[nt][2] + accB[nt][2], accA[nt][3] + accB[nt][3]);
+  }
+}
+
+// hidden-side vectors of the thread's two items -> item-major block [item][H]: H/2 64-bit stores per item
+template <int H>
+__device__ __forceinline__ void store_hid(float* blk, const int (&item)[2], const float (&x)[H][2]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float* p = blk + item[h] * H;
+#pragma unroll
+    for (int o = 0; o < H; o += 2) *reinterpret_cast<float2*>(p + o) = make_float2(x[o][h], x[o + 1][h]);
   }
 }
 
 template <int L, int H, bool MULTI>
 __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a) {
   constexpr WLayout W = make_wlayout(L, H, MULTI);
-  constexpr FragLayout FL = make_frag_layout(L, H);
+  constexpr FragLayout FL = make_frag_layout(L, H, kFragTile2);
   constexpr int HP = pad4(H);
+  static_assert(H == 10, "item-major hid blocks: 10 floats per item");
   static_assert(H <= 16, "slope words hold 2H bits");
   using B = Bwd2Bar;
 
@@ -239,6 +271,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
   float* const s_hid_l = smem + a.sm.hid_l;
   float* const s_act = smem + a.sm.act;
   float* const s_red = smem + a.sm.red;
+  const float* const s_zrow = smem + a.sm.zrow;
+  float* const s_zc = smem + a.sm.zc;
   uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
   uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + a.sm.mbar);
   const int Epad = pad4(E);
@@ -263,6 +297,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
       st[w * Epad + e] = a.topo[src[w] + e];
     }
     for (int i = tid; i < N; i += T) s_ones_b[i] = 1.f;
+    if (tid < 4) s_zc[40 + 10 * tid] = 1.f;          // (1, 0) at every item offset of a chunk quarter: the constant-1 column
     for (int i = tid; i < E; i += T) s_ones_l[i] = 1.f;
     for (int s = tid; s < Ns; s += T)
       if ((int)a.topo[a.to.prim_of + s] == s)
@@ -281,11 +316,12 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
   __syncthreads();
   const int first_grid = blockIdx.x, grid_step = gridDim.x;
 
-  if (warp < PW) {
+  const int wrole = a.role[warp];
+  if (wrole < 0x80) {
     // =====================================================================================================
     // PRODUCERS
     // =====================================================================================================
-    const int p = tid;
+    const int p = wrole * 32 + lane;
     int slot[2], br[2], ext[2], e_in0[2], deg[2], e_full1[2], e_out0[2], e_out1[2];
     bool on[2], prim[2], is_gen[2];
 #pragma unroll
@@ -303,6 +339,9 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
       e_out1[h] = prim[h] ? (int)a.topo[a.to.out_e + sl] : 0;
       is_gen[h] = prim[h] && a.topo[a.to.gen_e + sl] > a.topo[a.to.gen_b + sl];
     }
+    // branch-free stores: a slot that does not own a bus writes to the first padding column / item (never read as
+    // a non-zero product: every wide row is zero there)
+    const int colb[2] = {prim[0] ? br[0] : N, prim[1] ? br[1] : N};
     // twin groups (2 or 4 adjacent, aligned slots of one bus): both slots of a thread belong to the same group
     const int gsz_t = on[0] ? (int)a.topo[a.to.gsz + slot[0]] : 1;
     const int lead_lane = gsz_t >= 2 ? lane - (p - (int)a.topo[a.to.prim_of + slot[0]] / 2) : lane;
@@ -378,7 +417,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
       }
 #pragma unroll
       for (int i = 0; i < L; ++i) { amr[i][0] = 0.f; amr[i][1] = 0.f; }
-      prod_sum<3>(s3, s_red, PW, red_parity);          // its barrier also publishes s_cst
+      prod_sum<3>(s3, s_red, PW, wrole, red_parity);          // its barrier also publishes s_cst
       const float sPset = s3[0], sPmin = s3[1], sPmax = s3[2];
       float pglob = __ldg(a.pglob + (size_t)grid * K + (K - 1));
 
@@ -426,11 +465,11 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
             s_trig[j] = d; s_trig[NbP + j] = sd; s_trig[2 * NbP + j] = cd;
           }
         }
-        prod_sum<1>(part, s_red, PW, red_parity);       // its barrier also publishes s_gdP and s_trig
+        prod_sum<1>(part, s_red, PW, wrole, red_parity);       // its barrier also publishes s_gdP and s_trig
         const float adj_pg = part[0] / (lo_branch ? 2.f * (sPset - sPmin) : 2.f * (sPmax - sPset));
 
         // ---------------- physics adjoint (b): per-line partials ----------------
-#pragma unroll 2
+#pragma unroll 1
         for (int e = p; e < E; e += PT) {
           const int fi = t_fr[e], ti = t_tr[e], fa = t_fa[e], ta = t_ta[e];
           const float vf = nx[fi], vt = nx[ti];
@@ -521,14 +560,9 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
           // slope words: the next pair's bus word and this pair's line words travel under the L-net adjoint
           if (qq < 2 && on[0])
             mbw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(act_k + a.a2.mask[qq]) + 2 * p));
-          uint2 mlw[kB2MaxWalk];
-#pragma unroll
-          for (int it = 0; it < kB2MaxWalk; ++it) {
-            mlw[it] = make_uint2(0u, 0u);
-            if (do_phi && it < maxwalk && on[0])
-              mlw[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(act_k + a.a2.mask[ql]) +
-                                                              (1 + it) * a.a2.NsM + 2 * p));
-          }
+          const uint2* const mlp = reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(act_k + a.a2.mask[ql]) + a.a2.NsM + 2 * p);
+          uint2 mlw = make_uint2(0u, 0u);     // slope word of the line walked in iteration 0; the next ones are fetched one iteration ahead
+          if (do_phi && maxwalk > 0 && on[0]) mlw = __ldg(mlp);
 
           // ---- output layer ----
           float d2[H][2];
@@ -541,7 +575,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
             row_axpy<H, HP, 2>(d2, gv, wln + W.ln_wo);
             wait_empty(5 + q);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) if (prim[h]) s_grow[q * NbP + br[h]] = gv[h];
+            for (int h = 0; h < 2; ++h) s_grow[q * NbP + colb[h]] = gv[h];
             signal(B::GROW_FULL + q);
           } else {
             // adj m' rows for the consumers (they live in the line blocks, free at this point of the step)
@@ -555,10 +589,17 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
                 for (int c = 0; c < 5; ++c) s_featp[c * EP + col] = __ldg(lr + c);
               }
             }
+            // (their padding columns hold stale line records; the constant-1 hidden column of the bias gradient
+            // is not zero there, so they are cleared: dump column N included, the slots without a bus write zeros too)
+            for (int i = p; i < L * (NbP - N); i += PT) {
+              const int r = i / (NbP - N);
+              s_adjm[r * NbP + N + (i - r * (NbP - N))] = 0.f;
+            }
+            {
+              float* p0 = s_adjm + colb[0];
+              float* p1 = s_adjm + colb[1];
 #pragma unroll
-            for (int i = 0; i < L; ++i) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) if (prim[h]) s_adjm[i * NbP + br[h]] = amr[i][h];
+              for (int i = 0; i < L; ++i) { *p0 = amr[i][0]; *p1 = amr[i][1]; p0 += NbP; p1 += NbP; }
             }
             signal(B::ADJM_FULL);
 #pragma unroll
@@ -566,11 +607,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
           }
           apply_slope<H>(d2, mb, H);
           wait_empty(B2_D2L);
-#pragma unroll
-          for (int o = 0; o < H; ++o) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) if (prim[h]) s_hid[B2_D2L][o * NbP + br[h]] = d2[o][h];
-          }
+          store_hid(s_hid[B2_D2L], colb, d2);
           signal(B::HID_FULL + B2_D2L);
           // ---- second layer ----
           float d1[H][2];
@@ -581,11 +618,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
           }
           apply_slope<H>(d1, mb, 0);
           wait_empty(B2_D1L);
-#pragma unroll
-          for (int o = 0; o < H; ++o) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) if (prim[h]) s_hid[B2_D1L][o * NbP + br[h]] = d1[o][h];
-          }
+          store_hid(s_hid[B2_D1L], colb, d1);
           signal(B::HID_FULL + B2_D1L);
           // ---- dX of the first layer: state adjoints, latent adjoint, aggregate adjoint (fused block) ----
 #pragma unroll
@@ -613,12 +646,13 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
             for (int o = 0; o < H; ++o) { adjP[o][0] = 0.f; adjP[o][1] = 0.f; }
             wait_empty(B2_D2LN);
             wait_empty(B2_D1LN);
-#pragma unroll
-            for (int it = 0; it < kB2MaxWalk; ++it) {
-              if (it < warp_max_deg) {
-                const float* wp = wphi + opaque_zero();     // keep the weight rows in shared memory (no CSE into spills)
+#pragma unroll 1
+            for (int it = 0; it < warp_max_deg; ++it) {
+              {
+                const float* wp = wphi + opaque_zero();     // keep the weight rows in shared memory (no hoisting into spills)
                 const bool live[2] = {it < deg[0], it < deg[1]};
-                const uint32_t ml[2] = {mlw[it].x, mlw[it].y};
+                const uint32_t ml[2] = {mlw.x, mlw.y};
+                if (it + 1 < maxwalk && on[0]) mlw = __ldg(mlp + (size_t)(it + 1) * (a.a2.NsM / 2));
                 float e2[H][2], e1[H][2];
 #pragma unroll
                 for (int o = 0; o < H; ++o) { e2[o][0] = live[0] ? adjA[o][0] : 0.f; e2[o][1] = live[1] ? adjA[o][1] : 0.f; }
@@ -631,17 +665,9 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
                 apply_slope<H>(e1, ml, 0);
 #pragma unroll
                 for (int j = 0; j < H; ++j) { adjP[j][0] += e1[j][0]; adjP[j][1] += e1[j][1]; }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  if (live[h]) {
-                    const int col = t_inp[e_in0[h] + it];
-#pragma unroll
-                    for (int o = 0; o < H; ++o) {
-                      s_hid[B2_D2LN][o * EP + col] = e2[o][h];
-                      s_hid[B2_D1LN][o * EP + col] = e1[o][h];
-                    }
-                  }
-                }
+                const int coll[2] = {live[0] ? (int)t_inp[e_in0[0] + it] : E, live[1] ? (int)t_inp[e_in0[1] + it] : E};
+                store_hid(s_hid[B2_D2LN], coll, e2);
+                store_hid(s_hid[B2_D1LN], coll, e1);
               }
             }
             __syncwarp();
@@ -656,11 +682,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
               }
             }
             wait_empty(B2_ADJP);
-#pragma unroll
-            for (int o = 0; o < H; ++o) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) if (prim[h]) s_hid[B2_ADJP][o * NbP + br[h]] = adjP[o][h];
-            }
+            store_hid(s_hid[B2_ADJP], colb, adjP);
             signal(B::HID_FULL + B2_ADJP);
 #pragma unroll
             for (int i = 0; i < L; ++i) row_dot<H, HP, 2>(amr[i], adjP, wphi + W.phi_w1m + i * HP);
@@ -684,7 +706,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
     // =====================================================================================================
     // CONSUMERS
     // =====================================================================================================
-    const int cw = warp - PW;
+    const int cw = wrole & 0x7f;
     const bool issuer = cw == 0 && lane == 0;
     float* const gacc_w = a.gacc + ((size_t)blockIdx.x * CW + cw) * ((size_t)K * FL.step);
     const int nch_b = NbP / 16, nch_l = EP / 16;
@@ -702,53 +724,55 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
       __syncwarp();
       if (lane == 0) mbar_arrive(s_bar + bar);
     };
-    // activation block number b of this CTA -> global source
-    auto issue_act = [&](long long b) {
-      const long long stepi = b / NB;
-      const int r = (int)(b - stepi * NB);
-      const long long gi = stepi / K;
-      const int k = K - 1 - (int)(stepi - gi * K);
-      const long long grid = first_grid + gi * grid_step;
-      if (grid >= a.S) return;
+    // The issuing lane walks the activation blocks in consumption order: grid, step k = K-1..0, block r of the step
+    // (per pair in the order m, v, theta: h2L, h1L, A, and the per-line h1 of the pair's phi net).
+    long long ib_grid = first_grid;
+    int ib_k = K - 1, ib_r = 0;
+    auto issue_act = [&](int slot) {      // next block of the walk -> ring slot
+      if (ib_grid >= a.S) return;
+      const int r = ib_r;
       int qq, j;
       if (MULTI) { qq = r >> 2; j = r & 3; }
       else { qq = r < 9 ? r / 3 : 2; j = r - 3 * qq; }
       const int q = (qq == 0) ? 2 : qq - 1;
       const int off = j == 0 ? a.a2.h2L[q] : (j == 1 ? a.a2.h1L[q] : (j == 2 ? a.a2.A[q] : a.a2.h1line[MULTI ? q : 0]));
       const uint32_t bytes = (uint32_t)(H * (j == 3 ? EP : NbP) * 4);
-      const int slot = (int)(b % kB2ActSlots);
       mbar_expect_tx(s_bar + B::ACT_FULL + slot, bytes);
-      bulk_g2s(s_act + slot * ACTSZ, a.act + ((size_t)grid * K + k) * (size_t)a.a2.step + off, bytes, s_bar + B::ACT_FULL + slot);
+      bulk_g2s(s_act + slot * ACTSZ, a.act + ((size_t)ib_grid * K + ib_k) * (size_t)a.a2.step + off, bytes, s_bar + B::ACT_FULL + slot);
+      if (++ib_r == NB) {
+        ib_r = 0;
+        if (--ib_k < 0) { ib_k = K - 1; ib_grid += grid_step; }
+      }
     };
-    auto issue_state = [&](long long stepi) {
-      const long long gi = stepi / K;
-      const int k = K - 1 - (int)(stepi - gi * K);
-      const long long grid = first_grid + gi * grid_step;
-      if (grid >= a.S) return;
+    long long is_grid = first_grid;
+    int is_k = K - 1;
+    auto issue_state = [&]() {            // state entering the next step of the walk
+      if (is_grid >= a.S) return;
       mbar_expect_tx(s_bar + B::STATE_FULL, (uint32_t)((4 + L) * NbP * 4));
-      bulk_g2s(s_state, a.ck2 + ((size_t)grid * (K + 1) + k) * (size_t)a.a2.state, (uint32_t)((4 + L) * NbP * 4), s_bar + B::STATE_FULL);
+      bulk_g2s(s_state, a.ck2 + ((size_t)is_grid * (K + 1) + is_k) * (size_t)a.a2.state, (uint32_t)((4 + L) * NbP * 4), s_bar + B::STATE_FULL);
+      if (--is_k < 0) { is_k = K - 1; is_grid += grid_step; }
     };
-    long long b = 0, stepi = 0;
     if (issuer) {
       for (int i = 0; i < kB2ActSlots; ++i) issue_act(i);
-      issue_state(0);
+      issue_state();
     }
-    // wait for activation block b; returns its shared-memory address
+    int aslot = 0;               // ring slot of the next activation block
+    uint32_t ph_act = 0;         // parity of the slot's next completion (ACT_FULL and ACT_EMPTY advance together)
+    // wait for the next activation block; returns its shared-memory address
     auto act_wait = [&]() {
-      const int slot = (int)(b % kB2ActSlots);
-      mbar_wait(s_bar + B::ACT_FULL + slot, (uint32_t)((b / kB2ActSlots) & 1));
-      return s_act + slot * ACTSZ;
+      mbar_wait(s_bar + B::ACT_FULL + aslot, (ph_act >> aslot) & 1u);
+      return s_act + aslot * ACTSZ;
     };
-    // all reads of block b by this warp are done; the issuing lane refills the slot with block b + ring size
+    // all reads of the block by this warp are done; the issuing lane refills the slot once every warp is done
     auto act_done = [&]() {
-      const int slot = (int)(b % kB2ActSlots);
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_bar + B::ACT_EMPTY + slot);
+      if (lane == 0) mbar_arrive(s_bar + B::ACT_EMPTY + aslot);
       if (issuer) {
-        mbar_wait(s_bar + B::ACT_EMPTY + slot, (uint32_t)((b / kB2ActSlots) & 1));
-        issue_act(b + kB2ActSlots);
+        mbar_wait(s_bar + B::ACT_EMPTY + aslot, (ph_act >> aslot) & 1u);
+        issue_act(aslot);
       }
-      ++b;
+      ph_act ^= 1u << aslot;
+      aslot = aslot == kB2ActSlots - 1 ? 0 : aslot + 1;
     };
 
     for (long long grid = first_grid; grid < a.S; grid += grid_step) {
@@ -763,16 +787,15 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
           const bool do_phi = MULTI || qq == 2;
           // ---- output layer: dWout, dbout ----
           {
-            const float* h2L = act_wait();
-            auto hid = [&](int c) { return c < H ? h2L + c * NbP : s_ones_b; };
+            const float* h2L = act_wait();       // item-major; the 11th column is the constant 1 (bias gradient)
             if (q == 2) {
               wait_full(5);
-              cons_call<H + 1, L>(hid, [&](int r) { return s_adjm + r * NbP; }, nch_b, cw, CW, gln + FL.out);
+              cons_call<H + 1, L>(h2L, [&](int r) { return s_adjm + r * NbP; }, s_zrow, s_zc, nch_b, cw, CW, gln + FL.out);
               release(B::HID_EMPTY + B2_D2LN);
               release(B::HID_EMPTY + B2_D1LN);
             } else {
               wait_full(6 + q);
-              cons_call<H + 1, 1>(hid, [&](int) { return s_grow + q * NbP; }, nch_b, cw, CW, gln + FL.out);
+              cons_call<H + 1, 1>(h2L, [&](int) { return s_grow + q * NbP; }, s_zrow, s_zc, nch_b, cw, CW, gln + FL.out);
               release(B::GROW_EMPTY + q);
             }
             act_done();
@@ -781,8 +804,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
           {
             const float* h1L = act_wait();
             wait_full(B2_D2L);
-            cons_call<H, H + 1>([&](int c) { return s_hid[B2_D2L] + c * NbP; },
-                                [&](int r) { return r < H ? h1L + r * NbP : s_ones_b; }, nch_b, cw, CW, gln + FL.w2);
+            cons_call<H, H + 1>(s_hid[B2_D2L], [&](int r) { return r < H ? h1L + r * NbP : s_ones_b; }, s_zrow, s_zc, nch_b, cw,
+                                CW, gln + FL.w2);
             release(B::HID_EMPTY + B2_D2L);
             act_done();
           }
@@ -792,12 +815,12 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
             wait_full(B2_D1L);
             if (!have_state) { wait_full(8); have_state = true; }
             cons_call<H, 4 + L + H + 2>(
-                [&](int c) { return s_hid[B2_D1L] + c * NbP; },
+                s_hid[B2_D1L],
                 [&](int r) {
                   return r < 4 + L ? s_state + r * NbP
                                    : (r < 4 + L + H ? Ab + (r - 4 - L) * NbP : (r == 4 + L + H ? s_deg : s_ones_b));
                 },
-                nch_b, cw, CW, gln + FL.w1);
+                s_zrow, s_zc, nch_b, cw, CW, gln + FL.w1);
             release(B::HID_EMPTY + B2_D1L);
             act_done();
           }
@@ -805,27 +828,25 @@ __global__ void __launch_bounds__(384, 1) gns_backward2_kernel(const Bwd2Args a)
             // ---- phi net: per-line dW2 / db2 and dW1f over all lines at once, then dW1m / db1 per bus ----
             const float* h1n = act_wait();
             wait_full(B2_D2LN);
-            cons_call<H, H + 1>([&](int c) { return s_hid[B2_D2LN] + c * EP; },
-                                [&](int r) { return r < H ? h1n + r * EP : s_ones_l; }, nch_l, cw, CW, gphi + FL.w2l);
+            cons_call<H, H + 1>(s_hid[B2_D2LN], [&](int r) { return r < H ? h1n + r * EP : s_ones_l; }, s_zrow, s_zc, nch_l, cw,
+                                CW, gphi + FL.w2l);
             wait_full(B2_D1LN);
-            cons_call<H, 5>([&](int c) { return s_hid[B2_D1LN] + c * EP; }, [&](int r) { return s_featp + r * EP; }, nch_l, cw, CW,
-                            gphi + FL.w1f);
+            cons_call<H, 5>(s_hid[B2_D1LN], [&](int r) { return s_featp + r * EP; }, s_zrow, s_zc, nch_l, cw, CW, gphi + FL.w1f);
             release(B::HID_EMPTY + B2_D2LN);
             release(B::HID_EMPTY + B2_D1LN);
             act_done();
             wait_full(B2_ADJP);
-            cons_call<H, L + 1>([&](int c) { return s_hid[B2_ADJP] + c * NbP; },
-                                [&](int r) { return r < L ? s_state + (4 + r) * NbP : s_ones_b; }, nch_b, cw, CW, gphi + FL.w1m);
+            cons_call<H, L + 1>(s_hid[B2_ADJP], [&](int r) { return r < L ? s_state + (4 + r) * NbP : s_ones_b; }, s_zrow, s_zc,
+                                nch_b, cw, CW, gphi + FL.w1m);
             release(B::HID_EMPTY + B2_ADJP);
           }
         }  // pairs
         // the state rows of this step are dead: fetch those of the next one
         release(B::STATE_EMPTY);
-        ++stepi;
         if (issuer) {
           mbar_wait(s_bar + B::STATE_EMPTY, ph_sempty);
           ph_sempty ^= 1u;
-          issue_state(stepi);
+          issue_state();
         }
       }  // k
     }  // grid

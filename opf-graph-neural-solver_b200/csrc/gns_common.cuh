@@ -106,19 +106,26 @@ struct FragLayout { int w2l, w1f, w1m, out, w2, w1, net, step; };
 // hidden columns 8..10 for the 12 lanes that hold them (24 floats).  Columns 11..15 of the m16 tile are padding
 // and are never stored, which keeps the accumulators of 1,480 warps at 100 MB (< L2) instead of 145 MB.
 constexpr int kFragTile = 64 + 24;
+// The warp-specialised kernel (gns_backward2.cuh) maps MMA row g to hidden column 2g and row g+8 to column 2g+1, so a
+// lane holds 4 cells of one 8-row tile and adds them with ONE 128-bit reduction: [lane = (c/2)*4 + (r%8)/2][4], lanes
+// of hidden columns 0..11 only (24 lanes).
+constexpr int kFragTile2 = 24 * 4;
 __host__ __device__ constexpr int frag_tiles(int rows) { return (rows + 7) / 8; }
-__host__ __device__ constexpr FragLayout make_frag_layout(int L, int H) {
+__host__ __device__ constexpr FragLayout make_frag_layout(int L, int H, int tile = kFragTile) {
   FragLayout f{};
   int o = 0;
-  f.w2l = o; o += kFragTile * frag_tiles(H + 1);
-  f.w1f = o; o += kFragTile * frag_tiles(5);
-  f.w1m = o; o += kFragTile * frag_tiles(L + 1);
-  f.out = o; o += kFragTile * frag_tiles(L);
-  f.w2 = o; o += kFragTile * frag_tiles(H + 1);
-  f.w1 = o; o += kFragTile * frag_tiles(4 + L + H + 2);
+  f.w2l = o; o += tile * frag_tiles(H + 1);
+  f.w1f = o; o += tile * frag_tiles(5);
+  f.w1m = o; o += tile * frag_tiles(L + 1);
+  f.out = o; o += tile * frag_tiles(L);
+  f.w2 = o; o += tile * frag_tiles(H + 1);
+  f.w1 = o; o += tile * frag_tiles(4 + L + H + 2);
   f.net = o;
   f.step = (3 * o + 31) & ~31;
   return f;
+}
+__host__ __device__ constexpr int frag2_index(int r, int c) {
+  return (r / 8) * kFragTile2 + ((c / 2) * 4 + (r % 8) / 2) * 4 + (c % 2) * 2 + (r % 2);
 }
 // position of cell (wide row r, hidden column c <= 10) inside a call's block
 __host__ __device__ constexpr int frag_index(int r, int c) {
@@ -165,7 +172,9 @@ __host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, in
 // the plan's in_pos column.  Per pair q:  h2L, h1L, A (H rows x NbP each), h1 of the phi net per line
 // (H rows x EP), and the LeakyReLU slope bits: row 0 = bits of (h1L, h2L) per slot, row 1+it = bits of
 // (h1, h2) of the it-th line the slot walks (bit o: h1[o] > 0, bit H+o: h2[o] > 0), MR = 1 + max walk rows x NsM.
-// The forward zero-fills the padding columns of the float blocks (0 x garbage must not be NaN).
+// h2L is stored ITEM-major ([item][H]): it is the hidden-side operand of the output-layer gradient (see cons_call).
+// The forward zero-fills the padding columns of the float blocks (0 x garbage must not be NaN); there is always at
+// least one padding column / item, which the backward kernel uses as the dump target of its branch-free stores.
 // ---------------------------------------------------------------------------------
 __host__ __device__ constexpr int mma_stride(int items) {
   int p = pad4(items);
@@ -180,7 +189,7 @@ struct Act2Layout {
 };
 __host__ __device__ inline Act2Layout make_act2_layout(int L, int H, int N, int Ns, int E, int maxwalk) {
   Act2Layout a{};
-  a.NbP = mma_stride(N); a.EP = mma_stride(E); a.NsM = pad4(Ns); a.MR = 1 + maxwalk;
+  a.NbP = mma_stride(N + 1); a.EP = mma_stride(E + 1); a.NsM = pad4(Ns); a.MR = 1 + maxwalk;
   int o = 0;
   for (int q = 0; q < 3; ++q) {
     a.h2L[q] = o; o += H * a.NbP;

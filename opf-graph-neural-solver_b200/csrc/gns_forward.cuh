@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             const int blk = rem / (H * pb); rem -= blk * (H * pb);       // blk = 3 q + {h2L, h1L, A}
             const int r = rem / pb, c = N + rem - r * pb;
             const int q = blk / 3, w = blk - 3 * q;
-            __stcs(base + (w == 0 ? a.a2.h2L[q] : (w == 1 ? a.a2.h1L[q] : a.a2.A[q])) + r * a.a2.NbP + c, 0.f);
+            if (w == 0) __stcs(base + a.a2.h2L[q] + c * H + r, 0.f);       // item-major block
+            else __stcs(base + (w == 1 ? a.a2.h1L[q] : a.a2.A[q]) + r * a.a2.NbP + c, 0.f);
           } else {
             rem -= nb;
             const int q = rem / (H * pl); rem -= q * (H * pl);
@@ -491,7 +492,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
           for (int o = 0; o < H; ++o) lrelu_vec<VG>(z2[o]);
           if constexpr (V3) {
             stg_rows<H, VG, false>(act_k + a.a2.h1L[q] + my_brank, a.a2.NbP, gstr2, zL);
-            stg_rows<H, VG, false>(act_k + a.a2.h2L[q] + my_brank, a.a2.NbP, gstr2, z2);
+            {   // h2 of the L-net, item-major: H consecutive floats per bus (hidden-side operand of dWout)
+              static_assert(H % 2 == 0, "64-bit stores");
+              float* hp = act_k + a.a2.h2L[q] + my_brank * H;
+#pragma unroll
+              for (int g = 0; g < VG; ++g)
+#pragma unroll
+                for (int o = 0; o < H; o += 2)
+                  __stcs(reinterpret_cast<float2*>(hp + (size_t)g * gstr2 + o), make_float2(z2[o][g], z2[o + 1][g]));
+            }
             uint32_t wb[VG];
 #pragma unroll
             for (int g = 0; g < VG; ++g) wb[g] = 0u;

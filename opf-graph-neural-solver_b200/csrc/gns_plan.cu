@@ -198,14 +198,19 @@ int bwd2_threads_limit() { return 384; }
 
 Bwd2Geom choose_bwd2(const gns_plan* plan, const ModelDims& md, long long S) {
   Bwd2Geom g{};
-  const int force = env_int("GNS_BWD2", -1);
-  if (force == 0 || S <= 0) return g;
+  // Opt-in (GNS_BWD2=1).  Measured on B200, case300 K=4, 16,384 grids (profiles/r02_bwd2_*): 17.8 ms against 16.6 ms of
+  // the first kernel - the producer side runs on 5 warps at the same ~0.13 instructions / cycle / warp as every warp of
+  // the other kernels, so the instruction savings (330 k instead of 428 k warp instructions per grid) do not pay for the
+  // lost warp-level parallelism.  Kept as the evidence of that experiment and as a second, independent implementation
+  // of the adjoint (parity tests run both).
+  const int force = env_int("GNS_BWD2", 0);
+  if (force != 1 || S <= 0) return g;
   if (md.H != 10 || (md.L != 10 && md.L != 20)) return g;           // instantiated dims (latent in registers: L <= 20)
   if (plan->max_walk > 4 || plan->max_walk < 1) return g;            // kB2MaxWalk
   const int min_slots = env_int("GNS_BWD2_MIN_SLOTS", 96);
   if (force != 1 && plan->Ns < min_slots) return g;                   // small grids: several grids per CTA (first kernel)
   const int PW = ((plan->Ns + 1) / 2 + 31) / 32;
-  const int CW = std::max(1, env_int("GNS_BWD2_CW", PW));
+  const int CW = std::max(1, env_int("GNS_BWD2_CW", std::max(1, (3 * PW + 4) / 5)));   // measured best: 3 consumer warps for 5 producers
   if (PW > 8 || CW > 8 || (PW + CW) * 32 > bwd2_threads_limit()) return g;
   g.a2 = make_act2_layout(md.L, md.H, plan->N, plan->Ns, plan->E, plan->max_walk);
   if (md.L * g.a2.NbP > 2 * md.H * g.a2.EP) return g;                // the adj m' rows live in the two line blocks
@@ -309,7 +314,7 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     // per-grid block checkpoints of the warp-specialised backward kernel (Act2Layout); the forward writes whole
     // CTA-batches, so the grid count is rounded up to its batch size
     const size_t Sg = (size_t)fwd.nbatch * fwd.G;
-    const FragLayout FL = make_frag_layout(md.L, md.H);
+    const FragLayout FL = make_frag_layout(md.L, md.H, kFragTile2);
     w.ckpt = o; o = align(o + Sg * (md.K + 1) * (size_t)b2.a2.state * 4);
     w.pglob = o; o = align(o + Sg * md.K * 4);
     w.act = o; o = align(o + Sg * md.K * (size_t)b2.a2.step * 4);

@@ -151,6 +151,35 @@ def pack_grids(bus, branch, gen, base_mva: float):
     return buses, lines, generators
 
 
+def pack_varying(buses: torch.Tensor, lines: torch.Tensor, generators: torch.Tensor):
+    """Compact form of a packed batch of ONE case: only Pd,Qd | r,x,b,tau,shift | vg,Pg differ between the samples
+    the reference generates (ref GNS/augment_grids.py:35-53); bus_i,type,Gs,Bs | f_bus,t_bus | bus_i,Pmax,Pmin,qg
+    are constants of the case and Pg_set is a copy of Pg (ref GNS/utils.py:38).  Returns
+    ``(bus_var [S,N,2], line_var [S,E,5], gen_var [S,Gn,2]), (bus_const [N,4], line_const [E,2], gen_const [Gn,4])``
+    - 2N+5E+2Gn floats per grid instead of 6N+7E+7Gn (11.2 KB instead of 20.6 KB for case300).  Raises if the
+    batch does not have that structure (``GNS.infer_host_compact`` expands it on the device)."""
+    b, l, g = buses, lines, generators
+    cb, cl, cg = b[0][:, [0, 1, 4, 5]], l[0][:, [0, 1]], g[0][:, [0, 1, 2, 5]]
+    if not (torch.equal(b[:, :, [0, 1, 4, 5]], cb.expand(b.shape[0], -1, -1)) and
+            torch.equal(l[:, :, [0, 1]], cl.expand(l.shape[0], -1, -1)) and
+            torch.equal(g[:, :, [0, 1, 2, 5]], cg.expand(g.shape[0], -1, -1)) and torch.equal(g[:, :, 3], g[:, :, 6])):
+        raise ValueError("pack_varying: the batch is not a set of perturbed samples of one case "
+                         "(constant columns differ between grids, or Pg_set != Pg)")
+    var = (b[:, :, 2:4].contiguous(), l[:, :, 2:7].contiguous(), g[:, :, [4, 6]].contiguous())
+    return var, (cb.contiguous(), cl.contiguous(), cg.contiguous())
+
+
+def expand_varying(var, const):
+    """Host inverse of ``pack_varying`` (what ``gns_expand_inputs`` does on the device)."""
+    (bv, lv, gv), (cb, cl, cg) = var, const
+    S = bv.shape[0]
+    b = torch.empty(S, cb.shape[0], 6); l = torch.empty(S, cl.shape[0], 7); g = torch.empty(S, cg.shape[0], 7)
+    b[:, :, [0, 1, 4, 5]] = cb; b[:, :, 2:4] = bv
+    l[:, :, [0, 1]] = cl; l[:, :, 2:7] = lv
+    g[:, :, [0, 1, 2, 5]] = cg; g[:, :, 4] = gv[:, :, 0]; g[:, :, 3] = gv[:, :, 1]; g[:, :, 6] = gv[:, :, 1]
+    return b, l, g
+
+
 def renumber_buses(case: dict):
     """Map arbitrary external bus numbers (e.g. the real IEEE-300 table goes up to 9533) to the
     contiguous 1..N the path requires; the reference has no such step and raises IndexError at

@@ -263,3 +263,56 @@ def test_gradient_layout_maps_cover_every_parameter_once(lib, L, multi):
             col = (i - offs[n]) % sizes[n][1]
             assert col >= 4 + L, (n, col)
     assert derived > 0
+
+
+def test_fragment_maps_are_injective(lib):
+    """Every packed weight the backward kernels write maps to its own accumulator cell, for both kernels' layouts."""
+    for name in (b"frag", b"frag2"):
+        for multi in (1, 0):
+            n = lib.gns_layout_export(name, 4, 20, 10, multi, None, 0)
+            assert n > 0
+            out = np.zeros(n, dtype=np.int32)
+            lib.gns_layout_export(name, 4, 20, 10, multi, out.ctypes.data, n)
+            used = out[out >= 0]
+            assert len(np.unique(used)) == len(used) and used.min() >= 0
+    # the two layouts carry the same set of packed entries
+    a = np.zeros(n, dtype=np.int32); b = np.zeros(n, dtype=np.int32)
+    lib.gns_layout_export(b"frag", 4, 20, 10, 0, a.ctypes.data, n)
+    lib.gns_layout_export(b"frag2", 4, 20, 10, 0, b.ctypes.data, n)
+    assert np.array_equal(a >= 0, b >= 0)
+
+
+def test_pack_varying_round_trip_and_rejection():
+    b, l, g, _ = pkg.data.make_batch(30, 6, seed=4)
+    var, const = pkg.data.pack_varying(b, l, g)
+    assert var[0].shape == (6, 30, 2) and var[1].shape == (6, 41, 5) and var[2].shape == (6, 6, 2)
+    b2, l2, g2 = pkg.data.expand_varying(var, const)
+    assert torch.equal(b, b2) and torch.equal(l, l2) and torch.equal(g, g2)
+    bad = l.clone(); bad[3, 0, 1] += 1.0           # another topology in grid 3
+    with pytest.raises(ValueError):
+        pkg.data.pack_varying(b, bad, g)
+
+
+def test_topology_check_on_host_tensors():
+    b, l, g, _ = pkg.data.make_batch(14, 3, seed=0)
+    f, t, gb = l[0, :, 0].numpy().astype(int) - 1, l[0, :, 1].numpy().astype(int) - 1, g[0, :, 0].numpy().astype(int) - 1
+    plan = _host_plan(f, t, gb, 14)
+    assert plan.matches_host(l, g) and plan.matches_host(l[1], g[1])
+    bad = l.clone(); bad[2, 5, 0] = 3.0 if bad[2, 5, 0] != 3.0 else 4.0
+    assert not plan.matches_host(bad, g)
+
+
+def test_copied_model_rebuilds_its_gradient_leaf():
+    import copy
+    m = pkg.GNS(latent_dim=10, hidden_dim=10, K=2, multiple_phi=True)
+    m.flat_parameters()
+    leaf = m._leaf()
+    assert m._leaf() is leaf
+    twin = copy.deepcopy(m)
+    twin.flat_parameters()
+    assert twin._leaf() is not leaf and twin._leaf_owner == id(twin)
+
+
+def test_unsupported_dims_fail_at_construction(lib):
+    with pytest.raises(ValueError):
+        pkg.GNS(latent_dim=7, hidden_dim=3, K=2)
