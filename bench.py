@@ -2,15 +2,19 @@
 """bench.py - GNS K-step message passing throughput on B200 (BASELINE.json metric).
 
 One "step" = one pass of the hot path over one batch of synthetic load-perturbed grids:
-  forward  (inference, no checkpoints)           -> `value`, grids/s
-  fwd+bwd  (training step: forward, backward of mean(total_loss), NCCL all-reduce of the
-            flat gradient when N > 1; optimizer excluded)              -> `fwd_bwd.value`
-Workload (config.workload): BASELINE.json configs[3]/[metric] - case300 (IEEE-sized synthetic
-topology, 300/411/69), K=4, latent 20, hidden 10, multiple_phi, 65536 grids per GPU (weak
-scaling: every rank processes its own batch, no data-path collective in inference).
+  forward  (inference, no checkpoints)                                  -> `value`, grids/s
+  fwd+bwd  (training step: forward, backward of mean(total_loss), NCCL all-reduce of the flat
+            gradient when N > 1; optimizer excluded)                    -> `fwd_bwd`, `roofline.fwd_bwd_frac`
+  end to end (pinned host buffers -> public API -> pinned host outputs) -> `e2e`
+Workload (config.workload): BASELINE.json configs[3] - case300 (IEEE-sized synthetic topology 300/411/69), K=4,
+latent 20, hidden 10, multiple_phi, 65536 grids per GPU (weak scaling: every rank its own batch, no data-path
+collective in inference).  The line also carries what BASELINE.json states beside it: `strong` (configs[2]: case118
+fwd+bwd with 16384 grids IN TOTAL split over the ranks, all-reduce inside the timed region; configs[3]: case300
+forward with 65536 grids in total), `stress` (configs[4]: case300 K=8 latent 64 fwd+bwd, batch 32768, N=1 only) and,
+for N > 1, `grad_parity` (all-reduced gradient of N shards against the 1-GPU gradient of the whole batch).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-    python bench.py --impl reference ...                           # CPU arm (oracle port, host cores)
+    python bench.py --impl reference ...                           # CPU arm (host cores)
     torchrun ... bench.py --gpus N ...                             # one rank per GPU
 
 Prints ONE JSON line on rank 0.
@@ -30,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 IEEE = {14: (20, 5), 30: (41, 6), 118: (186, 54), 300: (411, 69)}
+REF_PER_CORE = 77.0     # grids/s/core of the real reference on case300-sized grids, forward, 1 thread
 
 
 def flops_per_grid(n_bus, n_line, K, L, H, multi=True):
@@ -43,16 +48,27 @@ def io_bytes_per_grid(n_bus, n_line, n_gen):
     return 4 * (6 * n_bus + 7 * n_line + 7 * n_gen), 4 * (2 * n_bus + 2)
 
 
+def compact_bytes_per_grid(n_bus, n_line, n_gen):
+    return 4 * (2 * n_bus + 5 * n_line + 2 * n_gen)
+
+
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port timed like the reference runs (per-sample Python loop,
-# ref GNS/main.py:279-283), one single-threaded worker per host core.
+# ref GNS/main.py:279-283), one single-threaded worker per host core, PERSISTENT pool.
 # ------------------------------------------------------------------------------------------
-def _cpu_worker(job):
+_W = {}
+
+
+def _cpu_init():
     import torch
     torch.set_num_threads(1)
+    from oracle import gns_oracle  # noqa: F401  (imported once per worker, outside every timed region)
+
+
+def _cpu_job(job):
+    import torch
     from oracle import gns_oracle as orc
     params, buses, lines, gens, K, L, train = job
-    t0 = time.perf_counter()
     n = buses.shape[0]
     if train:
         leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
@@ -65,53 +81,58 @@ def _cpu_worker(job):
         with torch.no_grad():
             for i in range(n):
                 orc.gns_forward(params, buses[i], lines[i], gens[i], K=K, latent_dim=L, gamma=0.9, multiple_phi=True)
-    return n, time.perf_counter() - t0
+    return n
 
 
-def cpu_reference_run(case, K, L, sample, train, workers):
-    import multiprocessing as mp
-    import torch
-    import opf_graph_neural_solver_b200 as pkg
-    from oracle import gns_oracle as orc
-    params = orc.init_params(L, 10, K, True, seed=0)
-    buses, lines, gens, label = pkg.data.make_batch(case, sample, seed=1)
-    workers = max(1, min(workers, sample))
-    per = (sample + workers - 1) // workers
-    jobs = [(params, buses[i:i + per], lines[i:i + per], gens[i:i + per], K, L, train)
-            for i in range(0, sample, per)]
-    t0 = time.perf_counter()
-    if len(jobs) == 1:
-        res = [_cpu_worker(jobs[0])]
-    else:
-        with mp.get_context("fork").Pool(len(jobs)) as pool:
-            res = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    return sum(r[0] for r in res) / wall, wall, len(jobs), label
-
-
-def _nr_worker(job):
+def _nr_job(job):
     from oracle import newton_raphson as nr
     tables, idx = job
-    t0 = time.perf_counter()
     res = nr.newton_pf_batch(tables, idx)
-    return len(idx), sum(r[2] for r in res), time.perf_counter() - t0
+    return len(idx), sum(int(r[2]) for r in res)
 
 
-def nr_baseline(case, sample, workers):
-    """Restated Newton-Raphson (not pypower, which is not installable offline) on the same
-    synthetic samples, one single-threaded worker per host core (ref GNS/evaluate.py:31-40)."""
-    import multiprocessing as mp
-    import opf_graph_neural_solver_b200 as pkg
-    tables = pkg.data.augment(pkg.data.get_case(case)[0], sample, seed=1)
-    workers = max(1, min(workers, sample))
-    chunks = [list(range(i, sample, workers)) for i in range(workers)]
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(workers) as pool:
-        res = pool.map(_nr_worker, [(tables, c) for c in chunks])
-    wall = time.perf_counter() - t0
-    n, conv = sum(r[0] for r in res), sum(r[1] for r in res)
-    return {"value": n / wall, "unit": "grids/s", "cores": workers, "kind": "restated NR, not pypower",
-            "sample": f"{n} grids, tol 1e-8, max 10 iterations, flat start", "converged": conv}
+class CpuArm:
+    """Persistent worker pool (created and warmed before any clock starts) over the bounded sample."""
+
+    def __init__(self, case, K, L, sample, workers):
+        import multiprocessing as mp
+        import opf_graph_neural_solver_b200 as pkg
+        from oracle import gns_oracle as orc
+        self.case, self.K, self.L, self.sample = case, K, L, sample
+        self.workers = max(1, min(workers, sample))
+        self.params = orc.init_params(L, 10, K, True, seed=0)
+        self.buses, self.lines, self.gens, self.label = pkg.data.make_batch(case, sample, seed=1)
+        self.tables = pkg.data.augment(pkg.data.get_case(case)[0], sample, seed=1, nominal_taps=True)
+        self.pool = mp.get_context("fork").Pool(self.workers, initializer=_cpu_init)
+        per = (sample + self.workers - 1) // self.workers
+        self.slices = [(i, min(sample, i + per)) for i in range(0, sample, per)]
+        self.pool.map(_cpu_job, [self._job(a, min(b, a + 1), False) for a, b in self.slices])   # warm every worker
+
+    def _job(self, a, b, train):
+        return (self.params, self.buses[a:b], self.lines[a:b], self.gens[a:b], self.K, self.L, train)
+
+    def run(self, train):
+        t0 = time.perf_counter()
+        n = sum(self.pool.map(_cpu_job, [self._job(a, b, train) for a, b in self.slices]))
+        wall = time.perf_counter() - t0
+        return n / wall, wall
+
+    def newton_raphson(self):
+        """Restated Newton-Raphson (not pypower, which is not installable offline; ref GNS/evaluate.py:31-40) on the
+        same topology and load / generation perturbation with NOMINAL taps (the reference's recipe draws off-nominal
+        taps for every line, ref GNS/augment_grids.py:43-45, which leaves no solvable power flow on a meshed grid)."""
+        chunks = [list(range(a, b)) for a, b in self.slices]
+        t0 = time.perf_counter()
+        res = self.pool.map(_nr_job, [(self.tables, c) for c in chunks])
+        wall = time.perf_counter() - t0
+        n, conv = sum(r[0] for r in res), sum(r[1] for r in res)
+        return {"value": n / wall, "unit": "grids/s", "cores": self.workers, "kind": "restated NR, not pypower",
+                "sample": f"{n} grids (nominal taps), tol 1e-8, max 10 iterations, flat start", "converged": conv,
+                "all_converged": conv == n}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference_arm(args):
@@ -119,35 +140,36 @@ def run_reference_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     workers = os.cpu_count() or 1
-    sample = args.cpu_sample or max(workers * 4, 64)
-    vals = []
-    for _ in range(args.warmup if args.cpu_sample is None else 0):
-        cpu_reference_run(args.case, args.K, args.latent, min(sample, workers), False, workers)
-    steps = args.steps if args.cpu_sample is None else 1
-    for _ in range(steps):
-        gps, wall, used, label = cpu_reference_run(args.case, args.K, args.latent, sample, False, workers)
-        vals.append((gps, wall))
+    sample = max(args.cpu_sample or 256, 256)
+    arm = CpuArm(args.case, args.K, args.latent, sample, workers)
+    for _ in range(args.warmup):
+        arm.run(False)
+    vals = [arm.run(False) for _ in range(args.steps)]
     gps = statistics.median(v[0] for v in vals)
-    tr_gps, _, _, _ = cpu_reference_run(args.case, args.K, args.latent, max(sample // 2, used), True, workers)
-    E, Gn = IEEE[args.case]
+    tr = [arm.run(True) for _ in range(max(1, min(args.steps, 3)))]
+    tr_gps = statistics.median(v[0] for v in tr)
+    try:
+        nrb = arm.newton_raphson()
+    except Exception as ex:  # pragma: no cover
+        nrb = {"value": None, "error": str(ex)}
+    arm.close()
+    cb = {"value": gps, "unit": "grids/s", "cores": arm.workers, "kind": "port",
+          "sample": f"{sample} grids per step, per-sample loop like ref GNS/main.py:279-283, one 1-thread worker per core, "
+                    f"persistent pool warmed before the clock; oracle port (the Python reference cannot travel to the GPU box)",
+          "per_core": gps / arm.workers, "reference_per_core_survey": REF_PER_CORE,
+          "fwd_bwd_value": tr_gps, "fwd_bwd_per_core": tr_gps / arm.workers, "newton_raphson": nrb}
     line = {
         "impl": "reference", "metric": f"case{args.case}_K{args.K}_fwd_grids_per_s", "value": gps, "unit": "grids/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(v[1] for v in vals),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"case{args.case} ({label}) K={args.K} latent={args.latent} hidden=10 multiple_phi, "
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * statistics.median(v[1] for v in vals), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"case{args.case} ({arm.label}) K={args.K} latent={args.latent} hidden=10 multiple_phi, "
                                f"{sample} grids per step (bounded sample of the 65536-grid batch)"},
         "fwd_bwd": {"value": tr_gps, "unit": "grids/s"},
-        "cpu_baseline": {"value": gps, "unit": "grids/s", "cores": used, "kind": "port",
-                         "sample": f"{sample} grids, per-sample loop like ref GNS/main.py:279-283, one 1-thread worker per core; "
-                                   f"oracle port (the Python reference cannot travel to the GPU box)",
-                         "fwd_bwd_value": tr_gps},
+        "cpu_baseline": cb,
         "e2e": {"value": gps, "unit": "grids/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    try:
-        line["cpu_baseline"]["newton_raphson"] = nr_baseline(args.case, min(sample, max(workers * 2, 32)), workers)
-    except Exception as ex:  # pragma: no cover
-        line["cpu_baseline"]["newton_raphson"] = {"value": None, "error": str(ex)}
     print(json.dumps(line), flush=True)
 
 
@@ -201,6 +223,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import opf_graph_neural_solver_b200 as pkg
+    from opf_graph_neural_solver_b200 import model as gmodel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,23 +242,62 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = pkg.load_library()
+    BLG = pkg.get_BLG()
+    counters = gmodel.COUNTERS
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """W warm-up steps, then exactly `steps` steps between barrier + synchronize, CUDA events, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        k0 = counters["kernels"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        timed.launches += counters["kernels"] - k0
+        return ms / steps
+
+    timed.launches = 0
+
+    def make_model(K, L):
+        torch.manual_seed(0)
+        m = pkg.GNS(latent_dim=L, hidden_dim=10, K=K, gamma=0.9, multiple_phi=True).to(dev)
+        m.validate_topology = False          # checked once per workload below, outside the timed regions
+        return m
+
+    def device_batch(case, S, seed):
+        base = min(S, 8192)
+        b, l, g, label = pkg.data.make_batch(case, base, seed=seed)
+        rep = (S + base - 1) // base
+        host = [t.repeat(rep, 1, 1)[:S].contiguous() for t in (b, l, g)]
+        return host, label
+
+    # ---------------- headline workload: configs[3], weak scaling ----------------
     case, K, L, S = args.case, args.K, args.latent, args.batch
     E, Gn = IEEE[case]
-    torch.manual_seed(0)
-    model = pkg.GNS(latent_dim=L, hidden_dim=10, K=K, gamma=0.9, multiple_phi=True).to(dev)
-    model.validate_topology = False          # checked once below, outside the timed region
-    base = min(S, 8192)
-    b, l, g, label = pkg.data.make_batch(case, base, seed=1 + rank)
-    rep = (S + base - 1) // base
-    host = [t.repeat(rep, 1, 1)[:S].contiguous().pin_memory() for t in (b, l, g)]
+    model = make_model(K, L)
+    host, label = device_batch(case, S, 1 + rank)
+    host = [t.pin_memory() for t in host]
     buses, lines, gens = (t.to(dev) for t in host)
-    BLG = pkg.get_BLG()
     plan = model.plan_for(lines, gens, case)
     assert plan.matches(lines, gens)
+    var, const = pkg.data.pack_varying(*host)
+    var = tuple(t.pin_memory() for t in var)
     S_train = min(S, args.train_batch)
     tb, tl, tg = buses[:S_train], lines[:S_train], gens[:S_train]
-    flat_grad = None
 
     def fwd_step():
         with torch.no_grad():
@@ -252,46 +314,134 @@ def run_ours(args):
     out_host = [torch.empty(S, case).pin_memory(), torch.empty(S, case).pin_memory(),
                 torch.empty(S).pin_memory(), torch.empty(S).pin_memory()]
 
-    def e2e_step():   # public API on host buffers: chunked H2D / kernel / D2H pipeline
-        model.infer_host(host[0], host[1], host[2], out=out_host, chunk=8192)
+    def e2e_step():        # public API on host buffers, compact input format: chunked H2D / expand / kernel / D2H pipeline
+        model.infer_host_compact(var, const, out=out_host, chunk=args.e2e_chunk)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms / steps
+    def e2e_full_step():   # same with the reference's full rows
+        model.infer_host(host[0], host[1], host[2], out=out_host, chunk=args.e2e_chunk)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_fwd = timed(fwd_step, args.steps, args.warmup)
     ms_train = timed(train_step, args.steps, args.warmup)
+    model.zero_grad(set_to_none=True)
     ms_e2e = timed(e2e_step, max(2, args.steps // 2), 3)
+    ms_e2e_full = timed(e2e_full_step, max(2, args.steps // 2), 3)
     clocks = sampler.stop() if rank == 0 else None
 
-    # dominant-kernel duration, measured live with CUDA events around the C-ABI forward call on the
-    # launching stream (pack kernel + persistent kernel; the pack kernel is ~2 us)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    with torch.no_grad():
-        fwd_step(); torch.cuda.synchronize()
-        ev[0].record(); fwd_step(); ev[1].record(); torch.cuda.synchronize()
-    kern_ms = ev[0].elapsed_time(ev[1])
+    # dominant-kernel durations, measured live with CUDA events around the C-ABI calls on the launching stream
+    # (forward call = pack + fuse + persistent kernel, the first two ~2 us; training = the two persistent kernels + folds)
+    def one(fn):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        fn(); torch.cuda.synchronize()
+        ev[0].record(); fn(); ev[1].record(); torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1])
+    kern_ms = one(fwd_step)
+    kern_train_ms = one(train_step)
+    model.zero_grad(set_to_none=True)
+
+    # ---------------- pinned H2D ceiling of this box with all ranks copying at once ----------------
+    probe_bytes = 512 << 20
+    ph = torch.empty(probe_bytes, dtype=torch.uint8).pin_memory()
+    pd = torch.empty(probe_bytes, dtype=torch.uint8, device=dev)
+    pd.copy_(ph, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        pd.copy_(ph, non_blocking=True)
+    e1.record()
+    barrier()
+    h2d_gbs = 4 * probe_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    if world > 1:
+        t = torch.tensor([h2d_gbs], device=dev)
+        tl_ = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(tl_, t)
+        h2d_all = [float(x) for x in tl_]
+    else:
+        h2d_all = [h2d_gbs]
+    del ph, pd
+
+    # ---------------- strong scaling of the stated totals (BASELINE.json configs[2], configs[3]) ----------------
+    strong = {}
+    lo, hi = pkg.parallel.shard_range(args.strong_fwd_total, rank, world)
+    sb, sl, sg = buses[:hi - lo], lines[:hi - lo], gens[:hi - lo]
+
+    def strong_fwd():
+        with torch.no_grad():
+            model(sb, sl, sg, *BLG)
+    ms = timed(strong_fwd, args.steps, args.warmup)
+    strong["configs3_case300_fwd"] = {"total_grids": args.strong_fwd_total, "grids_per_gpu": hi - lo, "ms_per_step": ms,
+                                      "value": args.strong_fwd_total / (ms * 1e-3), "unit": "grids/s"}
+    c2 = 118
+    m118 = make_model(4, 20)
+    h118, label118 = device_batch(c2, args.strong_train_total, 11)
+    lo, hi = pkg.parallel.shard_range(args.strong_train_total, rank, world)
+    b118, l118, g118 = (t[lo:hi].to(dev) for t in h118)
+    p118 = m118.plan_for(l118, g118, c2)
+    assert p118.matches(l118, g118)
+
+    def strong_train():
+        m118.zero_grad(set_to_none=True)
+        out = m118(b118, l118, g118, *BLG)
+        (out[2].sum() / args.strong_train_total).backward()
+        if world > 1:
+            pkg.parallel.allreduce_gradients(m118.parameters())
+    ms = timed(strong_train, args.steps, args.warmup)
+    fl118 = flops_per_grid(c2, IEEE[c2][0], 4, 20, 10)
+    strong["configs2_case118_fwd_bwd"] = {"total_grids": args.strong_train_total, "grids_per_gpu": hi - lo, "ms_per_step": ms,
+                                          "value": args.strong_train_total / (ms * 1e-3), "unit": "grids/s",
+                                          "workload": f"case118 ({label118}) K=4 latent=20, gradient all-reduce inside the timed region",
+                                          "tflops_algorithmic_per_gpu": args.strong_train_total / world / (ms * 1e-3) * 3 * fl118 / 1e12}
+    del m118, b118, l118, g118
+
+    # ---------------- multi-GPU gradient parity: N shards + all-reduce == 1 GPU on the whole batch ----------------
+    grad_parity = None
+    if world > 1:
+        Sp = 1024 * world
+        hp, _ = device_batch(case, Sp, 77)          # same seed on every rank: identical global batch
+        mp_ = make_model(K, L)
+        lo, hi = pkg.parallel.shard_range(Sp, rank, world)
+        mp_.zero_grad(set_to_none=True)
+        out = mp_(hp[0][lo:hi].to(dev), hp[1][lo:hi].to(dev), hp[2][lo:hi].to(dev), *BLG)
+        (out[2].sum() / Sp).backward()
+        pkg.parallel.allreduce_gradients(mp_.parameters())
+        g_sharded = torch.cat([p.grad.reshape(-1) for p in mp_.parameters()]).clone()
+        if rank == 0:
+            mp_.zero_grad(set_to_none=True)
+            out = mp_(hp[0].to(dev), hp[1].to(dev), hp[2].to(dev), *BLG)
+            out[2].mean().backward()
+            g_single = torch.cat([p.grad.reshape(-1) for p in mp_.parameters()])
+            gmax = float(g_single.abs().max())
+            diff = float((g_sharded - g_single).abs().max())
+            grad_parity = {"grids": Sp, "max_abs_diff": diff, "max_abs_grad": gmax, "rel": diff / gmax,
+                           "ok": diff <= 1e-5 * gmax, "bound": "1e-5 * max|g|"}
+        barrier()
+        del mp_
+
+    # ---------------- stress config: case300 K=8 latent 64 fwd+bwd, batch 32768 (N = 1 only) ----------------
+    stress = None
+    if world == 1 and not args.no_stress:
+        Ks, Ls, Ss, micro = 8, 64, args.stress_batch, args.stress_micro
+        ms64 = make_model(Ks, Ls)
+        nb = (Ss + micro - 1) // micro
+
+        def stress_step():     # one training step of batch Ss in micro-batches (the checkpoints of 32768 grids are 79 GB)
+            ms64.zero_grad(set_to_none=True)
+            for i in range(nb):
+                a, b_ = i * micro, min(Ss, (i + 1) * micro)
+                out = ms64(buses[a:b_], lines[a:b_], gens[a:b_], *BLG)
+                (out[2].sum() / Ss).backward()          # gradients accumulate into the flat buffer
+        try:
+            ms = timed(stress_step, 2, 1)
+            fls = flops_per_grid(case, E, Ks, Ls, 10)
+            stress = {"workload": f"case300 K={Ks} latent={Ls} multiple_phi fwd+bwd, batch {Ss} in {nb} micro-batches of {micro}",
+                      "ms_per_step": ms, "value": Ss / (ms * 1e-3), "unit": "grids/s",
+                      "tflops_algorithmic": Ss / (ms * 1e-3) * 3 * fls / 1e12}
+        except RuntimeError as ex:  # pragma: no cover
+            stress = {"error": str(ex)[:200]}
+        del ms64
 
     if rank != 0:
         if world > 1:
@@ -299,6 +449,7 @@ def run_ours(args):
         return
     fl = flops_per_grid(case, E, K, L, 10)
     in_b, out_b = io_bytes_per_grid(case, E, Gn)
+    cin_b = compact_bytes_per_grid(case, E, Gn)
     peak_ffma = max(lib.gns_measure_ffma_flops(local, 20000), lib.gns_measure_ffma2_flops(local, 20000))
     peaks = {}
     try:
@@ -309,19 +460,29 @@ def run_ours(args):
     gps_fwd = world * S / (ms_fwd * 1e-3)
     gps_train = world * S_train / (ms_train * 1e-3)
     gps_e2e = world * S / (ms_e2e * 1e-3)
+    gps_e2e_full = world * S / (ms_e2e_full * 1e-3)
     ach = S * fl / (kern_ms * 1e-3) / 1e12
-    traffic = None
+    ach_train = S_train * 3 * fl / (kern_train_ms * 1e-3) / 1e12
+    if stress and "tflops_algorithmic" in stress:
+        stress["frac_of_fp32_peak"] = stress["tflops_algorithmic"] * 1e12 / peak_ffma
+    for v in strong.values():
+        if "tflops_algorithmic_per_gpu" in v:
+            v["frac_of_fp32_peak"] = v["tflops_algorithmic_per_gpu"] * 1e12 / peak_ffma
+    traffic_ncu = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("forward_dram_bytes_per_launch")
+        traffic_ncu = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
     info = plan.launch_info(S, K, L, 10, True)
+    info_b = plan.launch_info(S_train, K, L, 10, True, backward=True)
+    h2d_ceiling = sum(h2d_all) * 1e9 / cin_b
     cpu = None
-    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only; same code path as --impl reference
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--case", str(case),
-                                "--K", str(K), "--latent", str(L), "--cpu-sample", str(args.cpu_sample or 256)],
-                               capture_output=True, text=True, timeout=600,
+                                "--K", str(K), "--latent", str(L), "--cpu-sample", str(args.cpu_sample or 256),
+                                "--steps", "3", "--warmup", "1"],
+                               capture_output=True, text=True, timeout=900,
                                env={**os.environ, "CUDA_VISIBLE_DEVICES": "", "RANK": "0", "WORLD_SIZE": "1"})
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as ex:  # pragma: no cover
@@ -333,27 +494,42 @@ def run_ours(args):
         "config": {"workload": f"case{case} ({label}) K={K} latent={L} hidden=10 multiple_phi gamma=0.9, "
                                f"{S} grids per GPU per step (BASELINE.json configs[3])",
                    "l2": "inputs larger than L2 (%.0f MB per step)" % (S * in_b / 1e6),
-                   "parallelism": f"dp{world} (batch sharded, no data-path collective)", "launch": info},
+                   "parallelism": f"dp{world} (batch sharded, no data-path collective)", "launch": info,
+                   "launch_backward": info_b, "numa_bound": numa_bound},
         "fwd_bwd": {"metric": f"case{case}_K{K}_fwd_bwd_grids_per_s", "value": gps_train, "unit": "grids/s",
                     "ms_per_step": ms_train, "grids_per_gpu_per_step": S_train,
                     "tflops_algorithmic": gps_train * 3 * fl / 1e12 / world,
                     "frac_of_fp32_peak": gps_train * 3 * fl / world / peak_ffma,
                     "includes": "forward with checkpoints, backward, gradient all-reduce (N>1); optimizer excluded"},
         "roofline": {"bound": "fp32_ffma", "achieved": ach, "peak": peak_ffma / 1e12, "unit": "TFLOP/s",
-                     "frac": ach * 1e12 / peak_ffma, "traffic": traffic,
+                     "frac": ach * 1e12 / peak_ffma, "traffic": None,
+                     "traffic_ncu": traffic_ncu,
+                     "fwd_bwd_achieved": ach_train, "fwd_bwd_frac": ach_train * 1e12 / peak_ffma,
+                     "fwd_bwd_kernel_ms": kern_train_ms,
                      "peak_source": "measured here: max of the register-only FFMA and packed FFMA2 probes "
                                     "(MEASURED_PEAKS.json has no FP32 entry); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
                      "kernel_ms": kern_ms, "flop_per_grid": fl,
                      "hbm": {"achieved_gbs": S * (in_b + out_b) / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "frac": S * (in_b + out_b) / (kern_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured"}},
+        "strong": strong,
+        "stress": stress,
+        "grad_parity": grad_parity,
         "cpu_baseline": cpu,
-        "e2e": {"value": gps_e2e, "unit": "grids/s", "h2d_bytes_per_step": S * in_b, "d2h_bytes_per_step": S * out_b,
-                "ms_per_step": ms_e2e, "path": "pinned host tensors -> GNS.infer_host (8192-grid chunks, copy/compute overlap) -> pinned host outputs"},
-        # our kernels per call: forward = pack, fuse, gns_forward; backward = gns_backward, reduce, gather, unfuse, unpack
-        "gpu_launches": 3 * args.steps + 8 * args.steps + max(2, args.steps // 2) * 3 * ((S + 8191) // 8192),
+        "e2e": {"value": gps_e2e, "unit": "grids/s", "h2d_bytes_per_step": S * cin_b, "d2h_bytes_per_step": S * out_b,
+                "ms_per_step": ms_e2e,
+                "path": "pinned host tensors in the compact format (data.pack_varying: Pd,Qd | r,x,b,tau,shift | vg,Pg) -> "
+                        "GNS.infer_host_compact (%d-grid chunks:" % args.e2e_chunk + " H2D, gns_expand_inputs, forward, D2H on three streams) -> "
+                        "pinned host outputs",
+                "h2d_gbs_per_gpu_concurrent": h2d_all, "h2d_ceiling_grids_per_s": h2d_ceiling,
+                "frac_of_h2d_ceiling": gps_e2e / h2d_ceiling,
+                "full_rows": {"value": gps_e2e_full, "ms_per_step": ms_e2e_full, "h2d_bytes_per_step": S * in_b,
+                              "path": "GNS.infer_host on the reference's packed rows",
+                              "frac_of_h2d_ceiling": gps_e2e_full / (sum(h2d_all) * 1e9 / in_b)}},
+        # kernels launched through the C ABI inside the timed regions, counted at the call sites (model.COUNTERS):
+        # forward = pack, fuse, gns_forward; backward = gns_backward, reduce, gather, unfuse, unpack; + expand per chunk
+        "gpu_launches": timed.launches,
         "clocks": clocks,
     }
-    line["config"]["numa_bound"] = numa_bound
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -371,6 +547,12 @@ def main():
     ap.add_argument("--latent", type=int, default=20)
     ap.add_argument("--batch", type=int, default=65536, help="grids per GPU per forward step")
     ap.add_argument("--train-batch", type=int, default=16384, help="grids per GPU per training step")
+    ap.add_argument("--strong-fwd-total", type=int, default=65536, help="configs[3]: total grids split over the ranks")
+    ap.add_argument("--strong-train-total", type=int, default=16384, help="configs[2]: total case118 grids split over the ranks")
+    ap.add_argument("--stress-batch", type=int, default=32768)
+    ap.add_argument("--stress-micro", type=int, default=8192)
+    ap.add_argument("--no-stress", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=4096, help="grids per chunk of the host pipeline")
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -6,7 +6,9 @@ measurement (host-side PyTorch / numpy; not on the GPU hot path).
                    seeded ``numpy.random.default_rng`` (the reference uses unseeded ``np.random``)
 * ``case14``       the IEEE 14-bus table (standard public test case; same numbers as
                    ``data/case14/augmented_case14_0.pkl`` of the reference)
-* ``synthetic_case`` an IEEE-*sized* random topology for 30 / 118 / 300 buses: the real
+* ``case30``       the IEEE 30-bus table (MATPOWER / pypower ``case30``), pinned by a Newton-Raphson known answer
+* ``synthetic_case`` an IEEE-*sized* random topology for 118 / 300 buses (hub degree and parallel lines like the
+                   published systems): the real
                    tables ship with pypower, which is not available offline.
                    Results obtained on these are labelled "IEEE-sized synthetic topology".
 """
@@ -52,24 +54,103 @@ def case14():
     return _tables(np.array(bus, float), np.array(br, float), np.array(gen, float))
 
 
-def synthetic_case(n_bus: int, n_line: int | None = None, n_gen: int | None = None, seed: int = 0):
-    """IEEE-sized synthetic topology: seeded random spanning tree plus chords (parallel
-    lines allowed, no self loops), contiguous bus ids 1..n_bus, generators on distinct
-    buses, base values drawn from case14-like ranges."""
+def case30():
+    """IEEE 30-bus test case as shipped with MATPOWER / pypower (``case30``: 30 buses, 41 branches, 6 generators at
+    buses 1, 2, 22, 27, 23, 13; Alsac & Stott data) - what ``pypower.api.case30()`` returns in the reference
+    (ref GNS/augment_grids.py:1,8).  Entered by hand (pypower is not installable offline) and pinned by a
+    Newton-Raphson known-answer test: losses 2.444 MW, slack 25.97 MW, min |V| 0.961 at bus 8, angles -3.96 deg at
+    bus 19 / +1.48 deg at bus 13 (the published ``runpf`` result)."""
+    pd = {2: (21.7, 12.7), 3: (2.4, 1.2), 4: (7.6, 1.6), 7: (22.8, 10.9), 8: (30, 30), 10: (5.8, 2), 12: (11.2, 7.5),
+          14: (6.2, 1.6), 15: (8.2, 2.5), 16: (3.5, 1.8), 17: (9, 5.8), 18: (3.2, 0.9), 19: (9.5, 3.4), 20: (2.2, 0.7),
+          21: (17.5, 11.2), 23: (3.2, 1.6), 24: (8.7, 6.7), 26: (3.5, 2.3), 29: (2.4, 0.9), 30: (10.6, 1.9)}
+    bus = np.zeros((30, 6))
+    bus[:, 0] = np.arange(1, 31)
+    bus[:, 1] = 1
+    for b in (2, 13, 22, 23, 27):
+        bus[b - 1, 1] = 2
+    bus[0, 1] = 3
+    for b, (p, q) in pd.items():
+        bus[b - 1, 2], bus[b - 1, 3] = p, q
+    bus[4, 5], bus[23, 5] = 0.19, 0.04
+    br = [[1, 2, 0.02, 0.06, 0.03], [1, 3, 0.05, 0.19, 0.02], [2, 4, 0.06, 0.17, 0.02], [3, 4, 0.01, 0.04, 0],
+          [2, 5, 0.05, 0.2, 0.02], [2, 6, 0.06, 0.18, 0.02], [4, 6, 0.01, 0.04, 0], [5, 7, 0.05, 0.12, 0.01],
+          [6, 7, 0.03, 0.08, 0.01], [6, 8, 0.01, 0.04, 0], [6, 9, 0, 0.21, 0], [6, 10, 0, 0.56, 0], [9, 11, 0, 0.21, 0],
+          [9, 10, 0, 0.11, 0], [4, 12, 0, 0.26, 0], [12, 13, 0, 0.14, 0], [12, 14, 0.12, 0.26, 0], [12, 15, 0.07, 0.13, 0],
+          [12, 16, 0.09, 0.2, 0], [14, 15, 0.22, 0.2, 0], [16, 17, 0.08, 0.19, 0], [15, 18, 0.11, 0.22, 0],
+          [18, 19, 0.06, 0.13, 0], [19, 20, 0.03, 0.07, 0], [10, 20, 0.09, 0.21, 0], [10, 17, 0.03, 0.08, 0],
+          [10, 21, 0.03, 0.07, 0], [10, 22, 0.07, 0.15, 0], [21, 22, 0.01, 0.02, 0], [15, 23, 0.1, 0.2, 0],
+          [22, 24, 0.12, 0.18, 0], [23, 24, 0.13, 0.27, 0], [24, 25, 0.19, 0.33, 0], [25, 26, 0.25, 0.38, 0],
+          [25, 27, 0.11, 0.21, 0], [28, 27, 0, 0.4, 0], [27, 29, 0.22, 0.42, 0], [27, 30, 0.32, 0.6, 0],
+          [29, 30, 0.24, 0.45, 0], [8, 28, 0.06, 0.2, 0.02], [6, 28, 0.02, 0.06, 0.01]]
+    br7 = np.zeros((41, 7))
+    br7[:, :5] = br
+    # bus, Pmax, Pmin, Pg, Vg, Qg
+    gen = [[1, 80, 0, 23.54, 1, 0], [2, 80, 0, 60.97, 1, 0], [22, 50, 0, 21.59, 1, 0], [27, 55, 0, 26.91, 1, 0],
+           [23, 30, 0, 19.2, 1, 0], [13, 40, 0, 37, 1, 0]]
+    case = _tables(bus, br7, np.array(gen, float))
+    case["bus"][:, 7] = 1.0
+    return case
+
+
+def degree_profile(case: dict):
+    """Degree statistics of a case's topology (what drives the twin-slot split and the barrier skew of the kernels)."""
+    f, t = case["branch"][:, 0].astype(int), case["branch"][:, 1].astype(int)
+    n = case["bus"].shape[0]
+    deg = np.bincount(np.concatenate([f, t]), minlength=n + 1)[1:]
+    indeg = np.bincount(t, minlength=n + 1)[1:]
+    pairs = {}
+    for a, b in zip(np.minimum(f, t), np.maximum(f, t)):
+        pairs[(a, b)] = pairs.get((a, b), 0) + 1
+    return {"max_degree": int(deg.max()), "max_in_degree": int(indeg.max()), "mean_degree": float(deg.mean()),
+            "parallel_lines": int(sum(v - 1 for v in pairs.values())), "in_degree_hist": np.bincount(indeg).tolist()}
+
+
+# Published statistics of the IEEE tables the generator imitates (the tables themselves ship with pypower, which is
+# not available offline): the 118-bus system has 186 branches over 179 distinct bus pairs (7 parallel lines) and its
+# busiest bus (49) carries 12 branches; the 300-bus system's busiest buses carry about a dozen branches and it has a
+# handful of parallel lines.  (n_parallel, hub_degree) per size.
+_IEEE_SHAPE = {118: (7, 12), 300: (4, 12)}
+
+
+def synthetic_case(n_bus: int, n_line: int | None = None, n_gen: int | None = None, seed: int = 0,
+                   n_parallel: int | None = None, hub_degree: int | None = None):
+    """IEEE-sized synthetic topology: seeded random spanning tree, one hub grown to ``hub_degree`` branches,
+    ``n_parallel`` duplicated lines, then random chords (no self loops), contiguous bus ids 1..n_bus, generators on
+    distinct buses, base values drawn from case14-like ranges.  Hub degree and parallel-line count
+    default to the statistics of the IEEE system of that size (``_IEEE_SHAPE``)."""
     if n_line is None or n_gen is None:
         n_line, n_gen = IEEE_SIZES[n_bus]
     if n_line < n_bus:
         raise ValueError("need n_line >= n_bus (the reference indexes line vectors by bus number)")
+    if n_parallel is None or hub_degree is None:
+        dp, dh = _IEEE_SHAPE.get(n_bus, (0, 0))
+        n_parallel = dp if n_parallel is None else n_parallel
+        hub_degree = dh if hub_degree is None else hub_degree
     rng = np.random.default_rng(seed)
     order = rng.permutation(n_bus)
     f, t = [], []
     for i in range(1, n_bus):                       # spanning tree
         a, b = order[i], order[rng.integers(0, i)]
         f.append(min(a, b)); t.append(max(a, b))
-    while len(f) < n_line:                          # chords
+    if hub_degree:                                  # grow the busiest bus to the published maximum degree
+        deg = np.bincount(np.array(f + t), minlength=n_bus)
+        hub = int(deg.argmax())
+        while deg[hub] < hub_degree and len(f) < n_line - n_parallel:
+            o = int(rng.integers(0, n_bus))
+            if o != hub and (min(o, hub), max(o, hub)) not in set(zip(f, t)):
+                f.append(min(o, hub)); t.append(max(o, hub)); deg[hub] += 1
+    for _ in range(min(n_parallel, max(0, n_line - len(f)))):   # parallel lines (the real 118 / 300 tables have them)
+        j = int(rng.integers(0, len(f)))
+        while hub_degree and hub in (f[j], t[j]):
+            j = int(rng.integers(0, len(f)))
+        f.append(f[j]); t.append(t[j])
+    have = set(zip(f, t))
+    hub_id = hub if hub_degree else -1
+    while len(f) < n_line:                          # chords: new bus pairs, away from the hub
         a, b = rng.integers(0, n_bus, size=2)
-        if a != b:
-            f.append(min(a, b)); t.append(max(a, b))
+        lo, hi = int(min(a, b)), int(max(a, b))
+        if lo != hi and (lo, hi) not in have and hub_id not in (lo, hi):
+            f.append(lo); t.append(hi); have.add((lo, hi))
     idx = np.lexsort((t, f))                        # sorted by (f, t) like the IEEE tables
     f, t = np.array(f)[idx] + 1, np.array(t)[idx] + 1
     br = np.zeros((n_line, 7))
@@ -83,28 +164,37 @@ def synthetic_case(n_bus: int, n_line: int | None = None, n_gen: int | None = No
     bus[:, 1] = 1
     bus[gen_bus - 1, 1] = 2
     bus[gen_bus[0] - 1, 1] = 3
-    bus[:, 2] = rng.uniform(0.0, 100.0, n_bus) * (rng.uniform(size=n_bus) < 0.8)   # Pd (rescaled by augment)
-    bus[:, 3] = bus[:, 2] * rng.uniform(-0.1, 0.5, n_bus)                           # Qd
+    # Injections per bus shrink with the size of the system (x 1.2 / sqrt(n_bus)): with case14-like per-bus power the
+    # backbone lines of a 300-bus random tree would carry several p.u. and no power flow exists (a flat-start
+    # Newton-Raphson then diverges; with this scaling it converges in 4-7 iterations on nominal taps).
+    ps = min(1.0, 1.2 / np.sqrt(n_bus))
+    bus[:, 2] = ps * rng.uniform(0.0, 100.0, n_bus) * (rng.uniform(size=n_bus) < 0.8)   # Pd (rescaled by augment)
+    bus[:, 3] = bus[:, 2] * rng.uniform(-0.1, 0.5, n_bus)                                # Qd
     gen = np.zeros((n_gen, 6))
     gen[:, 0] = gen_bus
-    gen[:, 1] = rng.uniform(100.0, 330.0, n_gen)    # Pmax
-    gen[:, 2] = 0.0                                  # Pmin
+    gen[:, 1] = ps * rng.uniform(100.0, 330.0, n_gen)    # Pmax
+    gen[:, 2] = 0.0                                       # Pmin
     gen[:, 3] = gen[:, 1] * rng.uniform(0.2, 0.7, n_gen)
-    gen[:, 4] = rng.uniform(1.0, 1.1, n_gen)        # Vg
-    gen[:, 5] = rng.uniform(-17.0, 42.0, n_gen)     # Qg
+    gen[:, 4] = rng.uniform(1.0, 1.1, n_gen)             # Vg
+    gen[:, 5] = ps * rng.uniform(-17.0, 42.0, n_gen)     # Qg
     return _tables(bus, br, gen)
 
 
 def get_case(n_bus: int, seed: int = 0):
-    """case14 -> the IEEE table; 30/118/300 -> IEEE-sized synthetic topology (labelled)."""
+    """case14 / case30 -> the IEEE tables; 118 / 300 -> IEEE-sized synthetic topology (labelled)."""
     if n_bus == 14:
         return case14(), "IEEE case14"
+    if n_bus == 30 and seed == 0:
+        return case30(), "IEEE case30"
     return synthetic_case(n_bus, seed=seed), f"IEEE-sized synthetic topology ({n_bus} buses)"
 
 
-def augment(case: dict, n_samples: int, seed: int = 0):
+def augment(case: dict, n_samples: int, seed: int = 0, nominal_taps: bool = False):
     """Vectorised restatement of the perturbation loop of ref GNS/augment_grids.py:35-53.
-    Returns float64 tables ``bus [S,N,13]``, ``branch [S,E,13]``, ``gen [S,Gn,21]``."""
+    Returns float64 tables ``bus [S,N,13]``, ``branch [S,E,13]``, ``gen [S,Gn,21]``.
+    ``nominal_taps=True`` keeps the case's own tap ratios / phase shifts instead of drawing U(0.8, 1.2) / U(-0.2, 0.2)
+    for EVERY line like the reference does (ref :43-45): random off-nominal taps on all lines of a meshed grid leave
+    no solvable power flow, so the Newton-Raphson baseline is timed on the nominal-tap variant (labelled)."""
     rng = np.random.default_rng(seed)
     S = int(n_samples)
     bus = np.repeat(np.asarray(case["bus"], dtype=np.float64)[None], S, axis=0)
@@ -114,8 +204,9 @@ def augment(case: dict, n_samples: int, seed: int = 0):
     branch[:, :, _R] *= rng.uniform(0.9, 1.1, (S, E))
     branch[:, :, _X] *= rng.uniform(0.9, 1.1, (S, E))
     branch[:, :, _B] *= rng.uniform(0.9, 1.1, (S, E))
-    branch[:, :, _TAP] = rng.uniform(0.8, 1.2, (S, E))
-    branch[:, :, _SHIFT] = rng.uniform(-0.2, 0.2, (S, E))
+    tap, shift = rng.uniform(0.8, 1.2, (S, E)), rng.uniform(-0.2, 0.2, (S, E))     # drawn either way: same random stream
+    if not nominal_taps:
+        branch[:, :, _TAP], branch[:, :, _SHIFT] = tap, shift
     gen[:, :, _VG] *= rng.uniform(0.95, 1.05, (S, Gn))
     span = gen[:, :, _PMAX] - gen[:, :, _PMIN]
     # the reference draws Pg from U(Pmin + 0.25 span, 0.75 span)  (augment_grids.py:47-49)

@@ -51,6 +51,21 @@ class LearningBlock(nn.Module):
 COUNTERS = {"kernels": 0, "forward_calls": 0, "backward_calls": 0}
 
 
+def chunk_bounds(S: int, chunk: int):
+    """[start, stop) of the chunks of the host pipeline: the first ones are small (chunk/8, chunk/8, chunk/4, chunk/2)
+    so that the kernels start after a short first copy, the rest full size (per-chunk launch overhead amortised)."""
+    bounds, a = [], 0
+    for frac in (8, 8, 4, 2):
+        step = max(1, chunk // frac)
+        if S - a > chunk:
+            bounds.append((a, a + step))
+            a += step
+    while a < S:
+        bounds.append((a, min(S, a + chunk)))
+        a += chunk
+    return bounds
+
+
 def _run_forward(module, plan, need_grad, buses, lines, gens, flat):
     """One ``gns_forward`` call on device tensors; returns (v, theta, total, last, workspace)."""
     lib = _lib.load_library()
@@ -189,6 +204,14 @@ class GNS(nn.Module):
         self._topo_ok_key = None          # (ptr, version, shape) of the last device tensors that passed the topology check
         self._plans = {}                  # topology key -> TopologyPlan
         self._last_plan = None
+
+    def __getstate__(self):
+        # copies / pickles carry the parameters only: topology plans hold native handles, and the gradient leaf and
+        # its aliases belong to this instance (a copied leaf has no hook); all of them are rebuilt on first use
+        state = self.__dict__.copy()
+        state.update(_plans={}, _last_plan=None, _flat_leaf=None, _leaf_owner=None, _grad_flat=None, _grad_aliases=None,
+                     _topo_ok_key=None, _last_grad_flat=None)
+        return state
 
     # ------------------------------------------------------------------ parameters
     def _flat_ok(self):
@@ -349,8 +372,7 @@ class GNS(nn.Module):
             flat = self.flat_parameters()
             plan = None
             bad = torch.zeros(1, dtype=torch.int32, device=dev)     # set by the per-chunk topology checks
-            for i, a in enumerate(range(0, S, chunk)):
-                b = min(S, a + chunk)
+            for i, (a, b) in enumerate(chunk_bounds(S, chunk)):
                 slot = i % 2
                 with torch.cuda.stream(h2d):
                     if i >= 2:

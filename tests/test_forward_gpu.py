@@ -112,10 +112,10 @@ def test_heterogeneous_topology_in_a_batch_is_rejected(lib):
 
 
 def test_unsupported_dims_fail_loudly(lib):
-    model = pkg.GNS(latent_dim=7, hidden_dim=3, K=2).cuda()
-    buses, lines, gens, _ = pkg.data.make_batch(14, 2, seed=4)
-    with pytest.raises(RuntimeError, match="no fallback"):
-        model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+    with pytest.raises(ValueError, match="no fallback"):          # at construction, not at the first forward
+        pkg.GNS(latent_dim=7, hidden_dim=3, K=2)
+    # the C ABI refuses them as well
+    assert lib.gns_dims_supported(7, 3) == 0
 
 
 def test_negative_voltage_is_clamped_like_the_reference(lib):
@@ -135,9 +135,28 @@ def test_infer_host_streams_chunks_and_matches_forward(lib):
     buses, lines, gens, _ = pkg.data.make_batch(30, 1000, seed=6)
     with torch.no_grad():
         want = model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
-    got = model.infer_host(buses.pin_memory(), lines.pin_memory(), gens.pin_memory(), chunk=192)   # ragged last chunk
-    for g, w in zip(got, want):   # chunks may pick another launch geometry: same math, other summation order
-        assert g.device.type == "cpu" and torch.allclose(g, w.cpu(), rtol=1e-5, atol=1e-6)
+    hb, hl, hg = buses.pin_memory(), lines.pin_memory(), gens.pin_memory()
+    got = model.infer_host(hb, hl, hg, chunk=192)   # ragged last chunk
+    # chunk by chunk the pipeline runs exactly the kernel a device-resident call of that chunk runs: bit-identical
+    with torch.no_grad():
+        bounds = pkg.model.chunk_bounds(1000, 192)
+        assert bounds[0][0] == 0 and bounds[-1][1] == 1000 and all(x[1] == y[0] for x, y in zip(bounds, bounds[1:]))
+        for a, b in bounds:
+            per = model(buses[a:b].cuda(), lines[a:b].cuda(), gens[a:b].cuda(), *BLG)
+            for g, w in zip(got, per):
+                assert g.device.type == "cpu" and torch.equal(g[a:b], w.cpu())
+    for g, w in zip(got, want):   # the whole batch may pick another launch geometry: same math, other summation order
+        assert torch.allclose(g, w.cpu(), rtol=1e-4, atol=1e-5)
+    # compact input format (only the columns that vary between samples travel): same results, bit for bit
+    var, const = pkg.data.pack_varying(hb, hl, hg)
+    got2 = model.infer_host_compact(tuple(t.pin_memory() for t in var), const, chunk=192)
+    for g, w in zip(got2, got):
+        assert torch.equal(g, w)
+    # a batch whose topology changes after the first chunk is rejected (every chunk is checked)
+    bad = hl.clone()
+    bad[700, 3, 0], bad[700, 3, 1] = bad[700, 4, 0], bad[700, 4, 1]
+    with pytest.raises(ValueError):
+        model.infer_host(hb, bad.pin_memory(), hg, chunk=192)
 
 
 def test_reference_default_constructor_k30(lib):
