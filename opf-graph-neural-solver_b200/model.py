@@ -438,16 +438,38 @@ class GNS(nn.Module):
         buses_d, lines_d, gens_d = prep(buses), prep(lines), prep(generators)
         with torch.cuda.device(dev):
             flat = self.flat_parameters()
-            host = (lines, generators) if (in_dev.type == "cpu" and lines.dtype == torch.float32) else None
-            plan = self.plan_for(lines_d, gens_d, buses_d.shape[1], host=host)
             params = [p for p, _ in self._param_list]
             need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-            if need_grad and not self.per_parameter_autograd:
-                v, theta, total, last = _GNSFunction.apply(self, plan, True, buses_d, lines_d, gens_d, self._leaf())
-            elif need_grad:
-                v, theta, total, last = _GNSFunction.apply(self, plan, True, buses_d, lines_d, gens_d, flat, *params)
-            else:   # inference: no autograd bookkeeping at all
-                v, theta, total, last, _ = _run_forward(self, plan, False, buses_d, lines_d, gens_d, flat)
+
+            def run(plan, b, l, g):
+                if need_grad and not self.per_parameter_autograd:
+                    return _GNSFunction.apply(self, plan, True, b, l, g, self._leaf())
+                if need_grad:
+                    return _GNSFunction.apply(self, plan, True, b, l, g, flat, *params)
+                return _run_forward(self, plan, False, b, l, g, flat)[:4]     # inference: no autograd bookkeeping at all
+
+            host = (lines, generators) if (in_dev.type == "cpu" and lines.dtype == torch.float32) else None
+            try:
+                plan = self.plan_for(lines_d, gens_d, buses_d.shape[1], host=host)
+            except ValueError:
+                plan = None
+            if plan is not None:
+                v, theta, total, last = run(plan, buses_d, lines_d, gens_d)
+            else:
+                # Heterogeneous batch (the reference rebuilds its index tensors per sample, ref GNS/main.py:153, so a
+                # per-sample loop over different topologies just works there): group the grids by topology, run every
+                # group as one batched call on its own plan, and put the results back in input order.
+                S = buses_d.shape[0]
+                keys = torch.cat([lines_d[:, :, :2].reshape(S, -1), gens_d[:, :, 0]], dim=1)
+                _, inverse = torch.unique(keys, dim=0, return_inverse=True)
+                parts, order = [], []
+                for gi in range(int(inverse.max()) + 1):
+                    idx = (inverse == gi).nonzero().flatten()
+                    b, l, g = buses_d[idx], lines_d[idx], gens_d[idx]
+                    parts.append(run(self.plan_for(l, g, b.shape[1]), b, l, g))
+                    order.append(idx)
+                back = torch.argsort(torch.cat(order))
+                v, theta, total, last = (torch.cat([p[i] for p in parts])[back] for i in range(4))
         if in_dev != dev:
             v, theta, total, last = (t.to(in_dev) for t in (v, theta, total, last))
         if single:

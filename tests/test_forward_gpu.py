@@ -103,12 +103,14 @@ def test_duplicate_generator_buses_sum_like_the_reference(lib):
     _check_against_oracle(model, buses, lines, gens, "duplicate gen bus")
 
 
-def test_heterogeneous_topology_in_a_batch_is_rejected(lib):
+def test_plan_rejects_a_batch_of_another_topology(lib):
+    """One plan = one topology: the check the forward relies on (mixed batches are then split by topology, see
+    test_heterogeneous_topology_batch_is_grouped_and_matches_per_sample_calls)."""
     model = pkg.GNS(latent_dim=20, hidden_dim=10, K=2, multiple_phi=True).cuda()
     buses, lines, gens, _ = pkg.data.make_batch(14, 4, seed=4)
     lines = lines.clone(); lines[2, 3, 1] = 9.0
     with pytest.raises(ValueError, match="share one topology"):
-        model(buses.cuda(), lines.cuda(), gens.cuda(), *BLG)
+        model.plan_for(lines.cuda(), gens.cuda(), 14)
 
 
 def test_unsupported_dims_fail_loudly(lib):
@@ -192,3 +194,57 @@ def test_device_side_augmenter_feeds_the_kernel(lib):
     b, l, g = pkg.data.augment_pack_device(case, 300, seed=3, device="cuda")
     assert b.is_cuda and b.shape == (300, 118, 6)
     _check_against_oracle(model, b.cpu(), l.cpu(), g.cpu(), "device-augmented case118")
+
+
+def test_heterogeneous_topology_batch_is_grouped_and_matches_per_sample_calls(lib):
+    """A batch that mixes topologies (here: generator sets and one re-routed line) runs group by group; results and
+    gradients equal the reference-style per-sample loop (ref GNS/main.py:153 rebuilds the indices per sample)."""
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=3, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(14, 9, seed=8)
+    lines, gens = lines.clone(), gens.clone()
+    lines[2::3, 5, 1] = 7.0            # every third grid: line 5 ends at bus 7 instead
+    gens[1::3, 4, 0] = 9.0             # every third grid (shifted): the last generator sits at bus 9
+    b, l, g = buses.cuda(), lines.cuda(), gens.cuda()
+    out = model(b, l, g, *BLG)
+    out[2].mean().backward()
+    got = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    singles = [model(b[i], l[i], g[i], *BLG) for i in range(9)]
+    torch.stack([s[2] for s in singles]).mean().backward()
+    for k in range(4):
+        assert torch.allclose(out[k], torch.stack([s[k] for s in singles]), rtol=1e-5, atol=1e-6)
+    for n, p in model.named_parameters():
+        assert torch.allclose(got[n], p.grad, rtol=1e-4, atol=1e-6), n
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    for i in (0, 1, 2):                # and each kind against the oracle
+        ov, oth, otot, olast = orc.gns_forward(params, buses[i], lines[i], gens[i], K=3, latent_dim=20, gamma=0.9,
+                                               multiple_phi=True)
+        assert_bus_close(out[0][i], ov, f"v[{i}]"); assert_loss_close(out[2][i:i + 1], otot.reshape(1), f"total[{i}]")
+
+
+def test_non_contiguous_bus_numbers_run_after_renumbering(lib):
+    """The real IEEE-300 table numbers its buses up to 9533, on which the reference raises IndexError at ``m[dst]``
+    (ref GNS/main.py:153, quirk Q8); ``data.renumber_buses`` maps them to 1..N and the GPU path runs."""
+    case = pkg.data.case30()
+    ext = case["bus"][:, 0] * 37 + 1000                      # external numbering with gaps
+    lut = {int(i + 1): float(e) for i, e in enumerate(ext)}
+    wild = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in case.items()}
+    wild["bus"][:, 0] = ext
+    wild["branch"][:, 0] = [lut[int(x)] for x in case["branch"][:, 0]]
+    wild["branch"][:, 1] = [lut[int(x)] for x in case["branch"][:, 1]]
+    wild["gen"][:, 0] = [lut[int(x)] for x in case["gen"][:, 0]]
+    with pytest.raises(IndexError):                           # like the reference: ids outside 1..N cannot be indexed
+        aug = pkg.data.augment(wild, 2, seed=1)
+        b, l, g = pkg.data.pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
+        pkg.TopologyPlan.from_tensors(l, g, 30, device=-1)
+    fixed, ids = pkg.data.renumber_buses(wild)
+    assert np.array_equal(ids, ext.astype(np.int64))
+    aug = pkg.data.augment(fixed, 5, seed=1)
+    b, l, g = pkg.data.pack_grids(aug["bus"], aug["branch"], aug["gen"], aug["baseMVA"])
+    ref = pkg.data.augment(case, 5, seed=1)
+    rb, rl, rg = pkg.data.pack_grids(ref["bus"], ref["branch"], ref["gen"], ref["baseMVA"])
+    assert torch.equal(b, rb) and torch.equal(l, rl) and torch.equal(g, rg)
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=20, hidden_dim=10, K=4, gamma=0.9, multiple_phi=True).cuda()
+    _check_against_oracle(model, b, l, g, "renumbered case30")
