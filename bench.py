@@ -236,7 +236,7 @@ def run_ours(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local)
-    numa_bound = pkg.parallel.bind_to_gpu_numa_node(local) if world > 1 else False
+    numa_bound = pkg.parallel.bind_to_gpu_numa_node(local)      # pinned buffers on the GPU's NUMA node (host copies)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -354,13 +354,35 @@ def run_ours(args):
     e1.record()
     barrier()
     h2d_gbs = 4 * probe_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    # ... and with the results travelling the other way at the same time, in the workload's byte ratio (the copies of
+    # the two directions share the link: measured here, they do not simply overlap)
+    in_g, out_g = compact_bytes_per_grid(case, E, Gn), io_bytes_per_grid(case, E, Gn)[1]
+    n_out = int(probe_bytes * out_g / in_g) // 16 * 16
+    qh = torch.empty(n_out, dtype=torch.uint8).pin_memory()
+    qd = torch.empty(n_out, dtype=torch.uint8, device=dev)
+    s_out = torch.cuda.Stream(dev)
+    barrier()
+    e0.record()
+    s_out.wait_event(e0)
+    for _ in range(4):
+        pd.copy_(ph, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            qh.copy_(qd, non_blocking=True)
+    e2 = torch.cuda.Event(enable_timing=True)
+    e2.record(s_out)
+    torch.cuda.current_stream(dev).wait_event(e2)
+    e1.record()
+    barrier()
+    bidir_grids_per_s = 4 * (probe_bytes / in_g) / (e0.elapsed_time(e1) * 1e-3)      # this rank: grids/s the link can carry
+    del qh, qd
     if world > 1:
-        t = torch.tensor([h2d_gbs], device=dev)
+        t = torch.tensor([h2d_gbs, bidir_grids_per_s], device=dev)
         tl_ = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(tl_, t)
-        h2d_all = [float(x) for x in tl_]
+        h2d_all = [float(x[0]) for x in tl_]
+        bidir_all = [float(x[1]) for x in tl_]
     else:
-        h2d_all = [h2d_gbs]
+        h2d_all, bidir_all = [h2d_gbs], [bidir_grids_per_s]
     del ph, pd
 
     # ---------------- strong scaling of the stated totals (BASELINE.json configs[2], configs[3]) ----------------
@@ -518,15 +540,19 @@ def run_ours(args):
         "e2e": {"value": gps_e2e, "unit": "grids/s", "h2d_bytes_per_step": S * cin_b, "d2h_bytes_per_step": S * out_b,
                 "ms_per_step": ms_e2e,
                 "path": "pinned host tensors in the compact format (data.pack_varying: Pd,Qd | r,x,b,tau,shift | vg,Pg) -> "
-                        "GNS.infer_host_compact (%d-grid chunks:" % args.e2e_chunk + " H2D, gns_expand_inputs, forward, D2H on three streams) -> "
+                        "GNS.infer_host_compact (%d-grid chunks:" % args.e2e_chunk + " H2D, gns_forward_compact, D2H on three streams) -> "
                         "pinned host outputs",
                 "h2d_gbs_per_gpu_concurrent": h2d_all, "h2d_ceiling_grids_per_s": h2d_ceiling,
                 "frac_of_h2d_ceiling": gps_e2e / h2d_ceiling,
+                "link_ceiling_grids_per_s": sum(bidir_all), "frac_of_link_ceiling": gps_e2e / sum(bidir_all),
+                "link_ceiling_note": "all ranks copying a grid's compact inputs host->device and its outputs device->host at the "
+                                     "same time (pinned, 512 MiB probes): the ceiling of ANY pipeline on this box",
+
                 "full_rows": {"value": gps_e2e_full, "ms_per_step": ms_e2e_full, "h2d_bytes_per_step": S * in_b,
                               "path": "GNS.infer_host on the reference's packed rows",
                               "frac_of_h2d_ceiling": gps_e2e_full / (sum(h2d_all) * 1e9 / in_b)}},
         # kernels launched through the C ABI inside the timed regions, counted at the call sites (model.COUNTERS):
-        # forward = pack, fuse, gns_forward; backward = gns_backward, reduce, gather, unfuse, unpack; + expand per chunk
+        # forward = pack, fuse, gns_forward; backward = gns_backward, reduce, gather, unfuse, unpack; + topology check per chunk (full rows)
         "gpu_launches": timed.launches,
         "clocks": clocks,
     }

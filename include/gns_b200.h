@@ -81,6 +81,18 @@ int gns_forward(const gns_plan* plan, const float* params,
                 float* v, float* theta, float* total_loss, float* last_loss,
                 void* workspace, int64_t workspace_bytes, int need_grad, void* stream);
 
+/* Inference forward on the COMPACT input format (see gns_expand_inputs for the columns): the kernel reads
+ * bus_var [S][n_bus][2], line_var [S][n_line][5], gen_var [S][n_gen][2] directly and takes the constant columns from
+ * bus_const [n_bus][4] / gen_const [n_gen][4]; the topology is the plan's (line_const is not needed).  Same outputs,
+ * bit for bit, as gns_forward on the expanded rows; no checkpoints (need_grad = 0).  Replaces ref GNS/utils.py:17-41
+ * + GNS/main.py:140-202 for host batches of one case: 11.2 KB instead of 20.6 KB per case300 grid cross PCIe. */
+int gns_forward_compact(const gns_plan* plan, const float* params,
+                        const float* bus_var, const float* line_var, const float* gen_var,
+                        const float* bus_const, const float* gen_const,
+                        int64_t S, int K, int latent_dim, int hidden_dim, int multiple_phi, float gamma,
+                        float* v, float* theta, float* total_loss, float* last_loss,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Backward of  sum_s ( grad_total[s]*total_loss[s] + grad_last[s]*last_loss[s]
  *                      + <grad_v[s], v[s]> + <grad_theta[s], theta[s]> )
  * w.r.t. the parameters (the implicit autograd backward of the reference,

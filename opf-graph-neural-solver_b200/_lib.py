@@ -10,7 +10,7 @@ _LIB = None
 
 SYMBOLS = [
     "gns_plan_create", "gns_plan_destroy", "gns_plan_export", "gns_dims_supported",
-    "gns_param_count", "gns_workspace_bytes", "gns_forward", "gns_backward",
+    "gns_param_count", "gns_workspace_bytes", "gns_forward", "gns_forward_compact", "gns_backward",
     "gns_check_topology", "gns_check_topology_async", "gns_expand_inputs", "gns_launch_info", "gns_layout_export", "gns_adam_step", "gns_measure_ffma_flops", "gns_measure_ffma2_flops",
     "gns_last_error", "gns_version",
 ]
@@ -58,6 +58,9 @@ def load_library():
     lib.gns_forward.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32,
                                 vp, vp, vp, vp, vp, i64, i32, vp]
     lib.gns_forward.restype = i32
+    lib.gns_forward_compact.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32,
+                                        vp, vp, vp, vp, vp, i64, vp]
+    lib.gns_forward_compact.restype = i32
     lib.gns_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32,
                                  vp, vp, vp, vp, vp, vp, i64, vp]
     lib.gns_backward.restype = i32

@@ -213,11 +213,12 @@ extern "C" int gns_launch_info(const gns_plan* plan, int64_t S, int K, int L, in
   return 0;
 }
 
-extern "C" int gns_forward(const gns_plan* cplan, const float* params, const float* buses, const float* lines,
-                           const float* gens, int64_t S, int K, int L, int H, int multi, float gamma, float* v,
-                           float* theta, float* total_loss, float* last_loss, void* workspace,
-                           int64_t workspace_bytes, int need_grad, void* stream) {
+static int forward_impl(const gns_plan* cplan, const float* params, const float* buses, const float* lines,
+                        const float* gens, const float* cbus, const float* cgen, int64_t S, int K, int L, int H, int multi,
+                        float gamma, float* v, float* theta, float* total_loss, float* last_loss, void* workspace,
+                        int64_t workspace_bytes, int need_grad, void* stream) {
   gns_plan* plan = const_cast<gns_plan*>(cplan);
+  const bool compact = cbus != nullptr;
   if (!plan || !params || !buses || !lines || !gens || !v || !theta || !total_loss || !last_loss || !workspace) {
     set_error("gns_forward: null argument"); return -1;
   }
@@ -269,6 +270,8 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
   a.a2 = b2.a2;
   a.ck2 = a.ckpt;
   a.al = make_act_layout(H, multi ? 3 : 1, plan->Ns, plan->E, gf.G, (need_grad && !b2.ok) ? act_grid_major(gb) : true);
+  a.compact = compact ? 1 : 0;
+  a.cbus = cbus; a.cgen = cgen;
   a.use_tma = (gf.sm.stage_l != 0 && ((uintptr_t)buses % 16 == 0) && ((uintptr_t)lines % 16 == 0) &&
                ((uintptr_t)gens % 16 == 0)) ? 1 : 0;
   std::memcpy(a.grp_of_warp, gf.grp_of_warp, 32);
@@ -277,6 +280,23 @@ extern "C" int gns_forward(const gns_plan* cplan, const float* params, const flo
   e = launch(a, gf, st);
   if (e != cudaSuccess) { set_error(std::string("forward launch: ") + cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+extern "C" int gns_forward(const gns_plan* plan, const float* params, const float* buses, const float* lines,
+                           const float* gens, int64_t S, int K, int L, int H, int multi, float gamma, float* v,
+                           float* theta, float* total_loss, float* last_loss, void* workspace,
+                           int64_t workspace_bytes, int need_grad, void* stream) {
+  return forward_impl(plan, params, buses, lines, gens, nullptr, nullptr, S, K, L, H, multi, gamma, v, theta, total_loss,
+                      last_loss, workspace, workspace_bytes, need_grad, stream);
+}
+
+extern "C" int gns_forward_compact(const gns_plan* plan, const float* params, const float* bus_var, const float* line_var,
+                                   const float* gen_var, const float* bus_const, const float* gen_const, int64_t S, int K,
+                                   int L, int H, int multi, float gamma, float* v, float* theta, float* total_loss,
+                                   float* last_loss, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!bus_const || (plan && plan->Gn > 0 && !gen_const)) { set_error("gns_forward_compact: null constant block"); return -1; }
+  return forward_impl(plan, params, bus_var, line_var, gen_var, bus_const, gen_const ? gen_const : bus_const, S, K, L, H, multi,
+                      gamma, v, theta, total_loss, last_loss, workspace, workspace_bytes, 0, stream);
 }
 
 extern "C" int gns_backward(const gns_plan* cplan, const float* params, const float* buses, const float* lines,

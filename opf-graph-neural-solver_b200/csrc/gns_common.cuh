@@ -704,6 +704,9 @@ struct FwdArgs {
   ActLayout al;
   Act2Layout a2;           // GRADV = 3: per-grid checkpoints for the warp-specialised backward kernel
   float* ck2;              // [S][K+1][a2.state] state entering step k (k = 0..K-1) and the final state (K)
+  int compact;             // inference on the compact input format: buses / lines / gens point to [S][N][2] / [S][E][5] / [S][Gn][2]
+  const float* cbus;       // [N][4]  bus_i, type, Gs, Bs   (compact format: constants of the case)
+  const float* cgen;       // [Gn][4] bus_i, Pmax, Pmin, qg
   int use_tma;             // inputs 16-byte aligned and staging present: prefetch the next batch with cp.async.bulk
   unsigned char grp_of_warp[32];   // warp -> group of 32/NGQ consecutive bus slots
   SmemPlan sm;

@@ -91,6 +91,19 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const int e_out0 = prim ? (int)t_outb[sl] : 0, e_out1 = prim ? (int)t_oute[sl] : 0;
   const int j0 = prim ? (int)t_genb[sl] : 0, j1 = prim ? (int)t_gene[sl] : 0;
 
+  if (!GRAD && a.compact) {   // constant columns of the case, once per CTA (the per-batch unpack never touches these rows)
+    for (int i = tid; i < N * G; i += T) {
+      const int ext = i / G, gl = i - ext * G, sl2 = t_rank[ext];
+      smem[a.sm.busc + 2 * NG + sl2 * G + gl] = a.cbus[ext * 4 + 2];      // Gs
+      smem[a.sm.busc + 3 * NG + sl2 * G + gl] = a.cbus[ext * 4 + 3];      // Bs
+    }
+    for (int i = tid; i < Gn * G; i += T) {
+      const int j = i / G;
+      smem[a.sm.genc + 0 * GnG + i] = a.cgen[j * 4 + 1];                  // Pmax
+      smem[a.sm.genc + 1 * GnG + i] = a.cgen[j * 4 + 2];                  // Pmin
+      smem[a.sm.genc + 4 * GnG + i] = a.cgen[j * 4 + 3];                  // qg
+    }
+  }
   // ---- TMA staging: the raw rows of batch b+gridDim are bulk-copied while batch b computes ----
   float* const s_raw_b = smem + a.sm.stage_b;
   float* const s_raw_l = smem + a.sm.stage_l;
@@ -99,18 +112,39 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
   const bool tma = a.use_tma != 0;
   uint32_t tma_phase = 0;
   // a batch takes the bulk path when it is full and its 16-byte windows stay inside the tensors
+  // Input rows: the reference's packed rows (6 / 7 / 7 floats), or - inference only - the compact format that carries
+  // just the columns that vary between the samples of a case (Pd,Qd | r,x,b,tau,shift | vg,Pg: 2 / 5 / 2 floats, see
+  // gns_forward_compact); the constant columns then come once per CTA from the per-case blocks a.cbus / a.cgen.
+  const bool compact = !GRAD && a.compact != 0;
+  const int cb = compact ? 2 : 6, cl = compact ? 5 : 7, cg = compact ? 2 : 7;     // floats per raw row
+  const int kb = compact ? 0 : 2, kl = compact ? 0 : 2;                             // first column kept
   auto bulk_ok = [&](int b) {
     const long long gb = (long long)b * G;
     if (!tma || gb + G > a.S) return false;
-    const BulkWindow wb = bulk_window(gb * N * 6, G * N * 6), wl = bulk_window(gb * E * 7, G * E * 7),
-                     wg = bulk_window(gb * Gn * 7, G * Gn * 7);
-    return wb.begin + wb.bytes <= a.S * N * 6 * 4 && wl.begin + wl.bytes <= a.S * E * 7 * 4 &&
-           wg.begin + wg.bytes <= a.S * Gn * 7 * 4;
+    const BulkWindow wb = bulk_window(gb * N * cb, G * N * cb), wl = bulk_window(gb * E * cl, G * E * cl),
+                     wg = bulk_window(gb * Gn * cg, G * Gn * cg);
+    return wb.begin + wb.bytes <= a.S * N * cb * 4 && wl.begin + wl.bytes <= a.S * E * cl * 4 &&
+           wg.begin + wg.bytes <= a.S * Gn * cg * 4;
+  };
+  // compact generator rows (vg, Pg) -> vg, and Pg twice: Pg_set is a copy of Pg (ref GNS/utils.py:38)
+  auto unpack_gens_compact = [&](const float* raw, long long g0, bool from_global) {
+    for (int idx = tid; idx < Gn * G; idx += T) {
+      const int gl = idx / Gn, j = idx - gl * Gn;
+      const float* src = raw + (size_t)idx * 2;
+      if (from_global) {
+        long long g = g0 + gl;
+        if (g >= a.S) g = a.S - 1;
+        src = raw + ((size_t)g * Gn + j) * 2;
+      }
+      const float vg = src[0], pg = src[1];
+      float* d = s_genc + j * G + gl;
+      d[3 * GnG] = vg; d[2 * GnG] = pg; d[5 * GnG] = pg;
+    }
   };
   auto bulk_issue = [&](int b) {     // one thread
     const long long gb = (long long)b * G;
-    const BulkWindow wb = bulk_window(gb * N * 6, G * N * 6), wl = bulk_window(gb * E * 7, G * E * 7),
-                     wg = bulk_window(gb * Gn * 7, G * Gn * 7);
+    const BulkWindow wb = bulk_window(gb * N * cb, G * N * cb), wl = bulk_window(gb * E * cl, G * E * cl),
+                     wg = bulk_window(gb * Gn * cg, G * Gn * cg);
     mbar_expect_tx(s_mbar, wb.bytes + wl.bytes + wg.bytes);
     bulk_g2s(s_raw_b, reinterpret_cast<const char*>(a.buses) + wb.begin, wb.bytes, s_mbar);
     bulk_g2s(s_raw_l, reinterpret_cast<const char*>(a.lines) + wl.begin, wl.bytes, s_mbar);
@@ -165,13 +199,15 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     if (bulk_ok(batch)) {
       mbar_wait(s_mbar, tma_phase);
       tma_phase ^= 1;
-      unpack_block(s_raw_b + bulk_window(g0 * N * 6, 0).shift, s_busc, G, N, 6, 2, NG, t_rank);
-      unpack_block(s_raw_l + bulk_window(g0 * E * 7, 0).shift, s_linef, G, E, 7, 2, EG, nullptr);
-      unpack_block(s_raw_g + bulk_window(g0 * Gn * 7, 0).shift, s_genc, G, Gn, 7, 1, GnG, nullptr);
+      unpack_block(s_raw_b + bulk_window(g0 * N * cb, 0).shift, s_busc, G, N, cb, kb, NG, t_rank);
+      unpack_block(s_raw_l + bulk_window(g0 * E * cl, 0).shift, s_linef, G, E, cl, kl, EG, nullptr);
+      if (compact) unpack_gens_compact(s_raw_g + bulk_window(g0 * Gn * cg, 0).shift, g0, false);
+      else unpack_block(s_raw_g + bulk_window(g0 * Gn * 7, 0).shift, s_genc, G, Gn, 7, 1, GnG, nullptr);
     } else {
-      load_block(a.buses, s_busc, g0, a.S, G, N, 6, 2, NG, t_rank);
-      load_block(a.lines, s_linef, g0, a.S, G, E, 7, 2, EG, nullptr);
-      load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
+      load_block(a.buses, s_busc, g0, a.S, G, N, cb, kb, NG, t_rank);
+      load_block(a.lines, s_linef, g0, a.S, G, E, cl, kl, EG, nullptr);
+      if (compact) unpack_gens_compact(a.gens, g0, true);
+      else load_block(a.gens, s_genc, g0, a.S, G, Gn, 7, 1, GnG, nullptr);
     }
     __syncthreads();
     {   // staging buffers are free again: start the copy of this CTA's next batch

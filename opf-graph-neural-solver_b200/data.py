@@ -271,6 +271,22 @@ def expand_varying(var, const):
     return b, l, g
 
 
+def expand_varying_device(var, const, device="cuda"):
+    """``expand_varying`` on the device with the hand-written kernel behind ``gns_expand_inputs`` (include/gns_b200.h):
+    compact device (or host) tensors -> the reference's packed rows on the GPU, e.g. to train on a compact data set."""
+    from . import _lib
+    lib = _lib.load_library()
+    dev = torch.device(device)
+    bv, lv, gv = (t.to(device=dev, dtype=torch.float32).contiguous() for t in var)
+    cb, cl, cg = (t.to(device=dev, dtype=torch.float32).contiguous() for t in const)
+    S, N, E, Gn = bv.shape[0], cb.shape[0], cl.shape[0], cg.shape[0]
+    b = torch.empty(S, N, 6, device=dev); l = torch.empty(S, E, 7, device=dev); g = torch.empty(S, Gn, 7, device=dev)
+    rc = lib.gns_expand_inputs(bv.data_ptr(), lv.data_ptr(), gv.data_ptr(), cb.data_ptr(), cl.data_ptr(), cg.data_ptr(), S, N, E,
+                               Gn, b.data_ptr(), l.data_ptr(), g.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "gns_expand_inputs")
+    return b, l, g
+
+
 def renumber_buses(case: dict):
     """Map arbitrary external bus numbers (e.g. the real IEEE-300 table goes up to 9533) to the
     contiguous 1..N the path requires; the reference has no such step and raises IndexError at

@@ -66,8 +66,10 @@ def chunk_bounds(S: int, chunk: int):
     return bounds
 
 
-def _run_forward(module, plan, need_grad, buses, lines, gens, flat):
-    """One ``gns_forward`` call on device tensors; returns (v, theta, total, last, workspace)."""
+def _run_forward(module, plan, need_grad, buses, lines, gens, flat, const=None):
+    """One ``gns_forward`` call on device tensors; returns (v, theta, total, last, workspace).
+    ``const`` = (bus_const, gen_const) device tensors: the three inputs are then in the compact format
+    (``gns_forward_compact``, inference only)."""
     lib = _lib.load_library()
     S, N = buses.shape[0], buses.shape[1]
     dev = buses.device
@@ -80,10 +82,17 @@ def _run_forward(module, plan, need_grad, buses, lines, gens, flat):
     v, theta = out[:S * N].view(S, N), out[S * N:2 * S * N].view(S, N)
     total, last = out[2 * S * N:2 * S * N + S], out[2 * S * N + S:]
     stream = torch.cuda.current_stream(dev).cuda_stream
-    rc = lib.gns_forward(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
-                         S, K, Ld, Hd, multi, float(module.gamma),
-                         v.data_ptr(), theta.data_ptr(), total.data_ptr(), last.data_ptr(),
-                         ws.data_ptr(), nbytes, int(need_grad), stream)
+    if const is not None:
+        assert not need_grad
+        rc = lib.gns_forward_compact(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
+                                     const[0].data_ptr(), const[1].data_ptr(), S, K, Ld, Hd, multi, float(module.gamma),
+                                     v.data_ptr(), theta.data_ptr(), total.data_ptr(), last.data_ptr(),
+                                     ws.data_ptr(), nbytes, stream)
+    else:
+        rc = lib.gns_forward(plan.handle, flat.data_ptr(), buses.data_ptr(), lines.data_ptr(), gens.data_ptr(),
+                             S, K, Ld, Hd, multi, float(module.gamma),
+                             v.data_ptr(), theta.data_ptr(), total.data_ptr(), last.data_ptr(),
+                             ws.data_ptr(), nbytes, int(need_grad), stream)
     _lib.check(rc, "gns_forward")
     COUNTERS["kernels"] += 3
     COUNTERS["forward_calls"] += 1
@@ -339,7 +348,8 @@ class GNS(nn.Module):
     def infer_host_compact(self, var, const, out=None, chunk=8192, device=None):
         """Same pipeline on the compact format of ``data.pack_varying``: the host ships only the columns that vary
         between samples (Pd,Qd | r,x,b,tau,shift | vg,Pg: 11.2 KB instead of 20.6 KB per case300 grid) and one
-        constant block per case; ``gns_expand_inputs`` rebuilds the reference's rows on the device."""
+        constant block per case; the forward kernel reads the compact rows directly (``gns_forward_compact``) and
+        takes the constant columns from the per-case block."""
         return self._infer_pipeline(tuple(var), tuple(const), out, chunk, device)
 
     def _infer_pipeline(self, host_in, const, out, chunk, device):
@@ -359,45 +369,44 @@ class GNS(nn.Module):
         with torch.cuda.device(dev):
             comp = torch.cuda.current_stream(dev)
             h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            NS = 3                                     # device staging slots
             dbuf = [[torch.empty((chunk,) + tuple(t.shape[1:]), dtype=torch.float32, device=dev) for t in host_in]
-                    for _ in range(2)]
+                    for _ in range(NS)]
+            cdev = None
             if const is not None:
-                cdev = [t.to(device=dev, dtype=torch.float32).contiguous() for t in const]
-                full = [torch.empty(chunk, n, c, dtype=torch.float32, device=dev) for n, c in ((N, 6), (E, 7), (Gn, 7))]
-            ready = [torch.cuda.Event() for _ in range(2)]
-            free = [torch.cuda.Event() for _ in range(2)]
+                # The forward kernel reads the compact rows directly (gns_forward_compact); the constants of the case
+                # are checked against the plan once: the plan is built from them.
+                cb, cl, cg = (t.to(device=dev, dtype=torch.float32).contiguous() for t in const)
+                cdev = (cb, cg)
+                lines0 = torch.zeros(1, E, 7, dtype=torch.float32, device=dev); lines0[0, :, :2] = cl
+                gens0 = torch.zeros(1, Gn, 7, dtype=torch.float32, device=dev); gens0[0, :, 0] = cg[:, 0]
+                plan = self.plan_for(lines0, gens0, N)
+            else:
+                plan = None
+            ready = [torch.cuda.Event() for _ in range(NS)]
+            free = [torch.cuda.Event() for _ in range(NS)]
             keep = []
             start = torch.cuda.Event(); start.record(comp)
             h2d.wait_event(start)
             flat = self.flat_parameters()
-            plan = None
             bad = torch.zeros(1, dtype=torch.int32, device=dev)     # set by the per-chunk topology checks
             for i, (a, b) in enumerate(chunk_bounds(S, chunk)):
-                slot = i % 2
+                slot = i % NS
                 with torch.cuda.stream(h2d):
-                    if i >= 2:
+                    if i >= NS:
                         h2d.wait_event(free[slot])
                     for dst, src in zip(dbuf[slot], host_in):
                         dst[:b - a].copy_(src[a:b], non_blocking=True)
                     ready[slot].record(h2d)
                 comp.wait_event(ready[slot])
                 d = [t[:b - a] for t in dbuf[slot]]
-                if const is not None:       # compact chunk -> packed rows (the constants are validated once, below)
-                    rc = lib.gns_expand_inputs(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), cdev[0].data_ptr(),
-                                               cdev[1].data_ptr(), cdev[2].data_ptr(), b - a, N, E, Gn, full[0].data_ptr(),
-                                               full[1].data_ptr(), full[2].data_ptr(), comp.cuda_stream)
-                    _lib.check(rc, "gns_expand_inputs")
-                    COUNTERS["kernels"] += 1
-                    free[slot].record(comp)
-                    d = [t[:b - a] for t in full]
                 if plan is None:
                     plan = self.plan_for(d[1], d[2], N)
                 elif self.validate_topology and const is None:
                     plan.check_async(d[1], d[2], bad)           # every chunk, without stalling the pipeline
                     COUNTERS["kernels"] += 1
-                res = _run_forward(self, plan, False, d[0], d[1], d[2], flat)[:4]
-                if const is None:
-                    free[slot].record(comp)
+                res = _run_forward(self, plan, False, d[0], d[1], d[2], flat, const=cdev)[:4]
+                free[slot].record(comp)          # the chunk's device buffers may be refilled
                 done = torch.cuda.Event(); done.record(comp)
                 d2h.wait_event(done)
                 with torch.cuda.stream(d2h):

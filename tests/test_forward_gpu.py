@@ -154,6 +154,9 @@ def test_infer_host_streams_chunks_and_matches_forward(lib):
     got2 = model.infer_host_compact(tuple(t.pin_memory() for t in var), const, chunk=192)
     for g, w in zip(got2, got):
         assert torch.equal(g, w)
+    # the device-side expansion of the compact format (gns_expand_inputs) rebuilds the packed rows bit for bit
+    eb, el, eg = pkg.data.expand_varying_device(var, const)
+    assert torch.equal(eb.cpu(), buses) and torch.equal(el.cpu(), lines) and torch.equal(eg.cpu(), gens)
     # a batch whose topology changes after the first chunk is rejected (every chunk is checked)
     bad = hl.clone()
     bad[700, 3, 0], bad[700, 3, 1] = bad[700, 4, 0], bad[700, 4, 1]
