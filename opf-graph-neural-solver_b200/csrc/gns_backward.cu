@@ -6,6 +6,7 @@
 
 #include "gns_backward.cuh"
 #include "gns_backward2.cuh"
+#include "gns_backward3.cuh"
 #include "gns_host.h"
 #include "../../include/gns_b200.h"
 
@@ -22,6 +23,11 @@ int make_bwd2_smem_floats(int L, int H, int E, int wstep, const Act2Layout& a2) 
   return make_bwd2_smem(L, H, E, wstep, a2).total;
 }
 
+int make_bwd3_smem_floats(int L, int H, int N, int E, int wstep, int nwarps, const Act2Layout& a2) {
+  return make_bwd3_smem(L, H, N, E, wstep, nwarps, a2).total;
+}
+int frag3_step_floats(int L, int H) { return make_frag_layout3(L, H).step; }
+
 int backward_ctas(const gns_plan* plan, const ModelDims&, const Geometry& g) {
   // one persistent CTA per SM slot; the exact occupancy is clamped again at launch
   return std::min(g.nbatch, plan->num_sms * std::max(1, (int)(plan->smem_optin / std::max<size_t>(g.smem_bytes, 1))));
@@ -33,11 +39,12 @@ int backward_ctas(const gns_plan* plan, const ModelDims&, const Geometry& g) {
 // gns_backward_kernel one to one.
 // `v2`: the warp-specialised kernel computes the scalar nets' output layer with the roles swapped (hid = [h2, 1],
 // one wide row = the output adjoint), so its cells are (row 0, column c) instead of (row r, column 0).
-std::vector<int32_t> build_frag_map(const ModelDims& md, bool v2) {
+std::vector<int32_t> build_frag_map(const ModelDims& md, int variant) {
+  const bool v2 = variant >= 2;
   const int L = md.L, H = md.H;
   const bool multi = md.multi != 0;
   const WLayout W = make_wlayout(L, H, multi);
-  const FragLayout F = make_frag_layout(L, H, v2 ? kFragTile2 : kFragTile);
+  const FragLayout F = variant == 3 ? make_frag_layout3(L, H) : make_frag_layout(L, H, v2 ? kFragTile2 : kFragTile);
   auto frag_index = [&](int r, int c) { return v2 ? gns::frag2_index(r, c) : gns::frag_index(r, c); };
   std::vector<int32_t> inv(W.wstep, -1);
   auto put = [&](int packed, int frag) { inv[packed] = frag; };
@@ -58,7 +65,9 @@ std::vector<int32_t> build_frag_map(const ModelDims& md, bool v2) {
         put(lb + (r < H ? W.ln_wo + r : W.ln_bo_s), fb + F.out + (v2 ? frag_index(0, r) : frag_index(r, 0)));
     } else {
       for (int r = 0; r < L; ++r)
-        for (int c = 0; c < H + 1; ++c) put(lb + (c < H ? W.ln_wo + r * W.HP + c : W.ln_bo_m + r), fb + F.out + frag_index(r, c));
+        for (int c = 0; c < H + 1; ++c)
+          put(lb + (c < H ? W.ln_wo + r * W.HP + c : W.ln_bo_m + r),
+              fb + F.out + (variant == 3 ? frag3_out_index(4 + r, c) : frag_index(r, c)));
     }
     for (int r = 0; r < H + 1; ++r)
       for (int c = 0; c < H; ++c) put(lb + (r < H ? W.ln_w2 + r * W.HP : W.ln_b2) + c, fb + F.w2 + frag_index(r, c));
@@ -73,8 +82,8 @@ std::vector<int32_t> build_frag_map(const ModelDims& md, bool v2) {
   return inv;
 }
 
-static const int32_t* get_frag_map(gns_plan* plan, const ModelDims& md, bool v2) {
-  auto key = std::make_tuple(md.L, md.H, md.multi + (v2 ? 2 : 0));
+static const int32_t* get_frag_map(gns_plan* plan, const ModelDims& md, int v2) {
+  auto key = std::make_tuple(md.L, md.H, md.multi + 2 * v2);
   auto it = plan->frag_maps.find(key);
   if (it != plan->frag_maps.end()) return it->second;
   const std::vector<int32_t> inv = build_frag_map(md, v2);
@@ -183,7 +192,7 @@ static int fold_gradients(gns_plan* plan, const ModelDims& md, const float* gacc
   const gns_plan::PackMap* pm = get_pack_map(plan, md);
   if (!pm) return -2;
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
-  const FragLayout FL = make_frag_layout(md.L, md.H, tile);
+  const FragLayout FL = tile == 0 ? make_frag_layout3(md.L, md.H) : make_frag_layout(md.L, md.H, tile);
   const size_t per_part = (size_t)md.K * FL.step;
   float* packed_grad = reinterpret_cast<float*>(wsb + ws.packed_grad);
   const int th = 256;
@@ -209,7 +218,7 @@ static int run_backward2(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2
   const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
   const FragLayout FL = make_frag_layout(md.L, md.H, kFragTile2);
   const size_t per_part = (size_t)md.K * FL.step;
-  const int32_t* d_inv = get_frag_map(plan, md, true);
+  const int32_t* d_inv = get_frag_map(plan, md, 2);
   if (!d_inv) return -2;
   const int nparts = b2.ctas * b2.CW;
   float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
@@ -250,6 +259,42 @@ static int run_backward2(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2
   return fold_gradients(plan, md, gacc, nparts, d_inv, a.params, wsb, ws, grad_params, st, kFragTile2);
 }
 
+// fragment-space kernel (gns_backward3.cuh)
+static int run_backward3(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2, const Workspace& ws, const float* buses,
+                         const float* lines, const float* gens, long long S, float gamma, const float* grad_total,
+                         const float* grad_last, const float* grad_v, const float* grad_theta, float* grad_params,
+                         char* wsb, cudaStream_t st) {
+  const WLayout W = make_wlayout(md.L, md.H, md.multi != 0);
+  const FragLayout FL = make_frag_layout3(md.L, md.H);
+  const size_t per_part = (size_t)md.K * FL.step;
+  const int32_t* d_inv = get_frag_map(plan, md, 3);
+  if (!d_inv) return -2;
+  const int nw = b2.T / 32;
+  const int nparts = b2.ctas * nw;
+  float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
+  cudaError_t e = cudaMemsetAsync(gacc, 0, (size_t)nparts * per_part * 4, st);
+  if (e != cudaSuccess) { set_error(std::string("memset gacc: ") + cudaGetErrorString(e)); return -2; }
+  Bwd3Launcher launch = find_backward3(md.L, md.H, md.multi);
+  if (!launch) { set_error("gns_backward: fragment-space kernel not built for these dims"); return -1; }
+  Bwd3Args a{};
+  a.params = reinterpret_cast<const float*>(wsb + ws.packed_params);
+  a.buses = buses; a.lines = lines; a.gens = gens;
+  a.ck2 = reinterpret_cast<const float*>(wsb + ws.ckpt);
+  a.pglob = reinterpret_cast<const float*>(wsb + ws.pglob);
+  a.act = reinterpret_cast<const float*>(wsb + ws.act);
+  a.grad_total = grad_total; a.grad_last = grad_last; a.grad_v = grad_v; a.grad_theta = grad_theta;
+  a.gacc = gacc;
+  a.topo = plan->d_topo;
+  a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K;
+  a.a2 = b2.a2;
+  a.sm = make_bwd3_smem(md.L, md.H, plan->N, plan->E, W.wstep, nw, b2.a2);
+  a.to = plan->to;
+  for (int k = 0; k < md.K; ++k) a.wk[k] = (float)std::pow((double)gamma, (double)(md.K - k));
+  e = launch(a, b2, plan->num_sms, st);
+  if (e != cudaSuccess) { set_error(std::string("backward3 launch: ") + cudaGetErrorString(e)); return -2; }
+  return fold_gradients(plan, md, gacc, nparts, d_inv, a.params, wsb, ws, grad_params, st, 0);
+}
+
 int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const float* buses, const float* lines,
                  const float* gens, long long S, float gamma, const float* grad_total, const float* grad_last,
                  const float* grad_v, const float* grad_theta, float* grad_params, void* workspace,
@@ -263,6 +308,9 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   const Workspace ws = plan_workspace(plan, md, S, true, gf, gb, b2);
   if (b2.ok) {
     if ((long long)ws.total > workspace_bytes) { set_error("gns_backward: workspace too small"); return -1; }
+    if (b2.variant == 3)
+      return run_backward3(plan, md, b2, ws, buses, lines, gens, S, gamma, grad_total, grad_last, grad_v, grad_theta,
+                           grad_params, static_cast<char*>(workspace), st);
     return run_backward2(plan, md, b2, ws, buses, lines, gens, S, gamma, grad_total, grad_last, grad_v, grad_theta,
                          grad_params, static_cast<char*>(workspace), st);
   }
@@ -271,7 +319,7 @@ int run_backward(gns_plan* plan, const ModelDims& md, const float* params, const
   const int nwarps = gb.T / 32;
   const FragLayout FL = make_frag_layout(md.L, md.H);
   const size_t per_part = (size_t)md.K * FL.step;
-  const int32_t* d_inv = get_frag_map(plan, md, false);
+  const int32_t* d_inv = get_frag_map(plan, md, 0);
   if (!d_inv) return -2;
   // GNS_DETERMINISTIC=0: the warps of a CTA share one accumulator block (10x smaller, L2 resident); the order of
   // their floating-point reductions is then not fixed, so gradients are reproducible to rounding only
@@ -325,8 +373,9 @@ extern "C" int gns_layout_export(const char* name, int K, int latent_dim, int hi
   std::vector<int32_t> v;
   const std::string n(name);
   if (n == "pack") v = build_pack_map(md);
-  else if (n == "frag") v = build_frag_map(md, false);
-  else if (n == "frag2") v = build_frag_map(md, true);
+  else if (n == "frag") v = build_frag_map(md, 0);
+  else if (n == "frag2") v = build_frag_map(md, 2);
+  else if (n == "frag3") v = build_frag_map(md, 3);
   else { set_error("gns_layout_export: unknown map '" + n + "'"); return -1; }
   if (out) {
     if (capacity < (int)v.size()) { set_error("gns_layout_export: capacity too small"); return -1; }

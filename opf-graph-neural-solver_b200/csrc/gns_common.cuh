@@ -230,6 +230,12 @@ struct TopoOffsets {      // offsets in uint16 units inside the index block
   // extension read by the warp-specialised backward kernel only (gns_backward2.cuh)
   int fr, tr;             // [E] bus rank of the from / to bus
   int ext_rank;           // [N] bus rank -> external bus
+  // lines as items (gns_backward3.cuh), indexed by the line's activation column c = in_pos
+  int col_slot, col_it;   // [E] slot that walks the line and its position in that slot's walk (address of the slope word)
+  int col_brank;          // [E] bus rank of the receiving bus
+  int col_line;           // [E] line id
+  int rin_b;              // [N+1] in-line range of the bus with this rank inside rin_cols
+  int rin_cols;           // [E] activation columns of the lines entering a bus, grouped by bus rank (ascending line id)
   int total_ext;          // padded to a multiple of 8
 };
 
@@ -261,6 +267,12 @@ __host__ __device__ inline TopoOffsets make_topo_offsets(int N, int Ns, int E, i
   t.fr = o; o += E;
   t.tr = o; o += E;
   t.ext_rank = o; o += N;
+  t.col_slot = o; o += E;
+  t.col_it = o; o += E;
+  t.col_brank = o; o += E;
+  t.col_line = o; o += E;
+  t.rin_b = o; o += N + 1;
+  t.rin_cols = o; o += E;
   t.total_ext = (o + 7) & ~7;
   return t;
 }

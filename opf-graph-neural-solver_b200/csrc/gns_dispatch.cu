@@ -39,4 +39,16 @@ Bwd2Launcher find_backward2(int L, int H, int multi) {
   }
   return nullptr;
 }
+Bwd3Launcher find_backward3_l10(int multi);
+Bwd3Launcher find_backward3_l20(int multi);
+Bwd3Launcher find_backward3_l64(int multi);
+Bwd3Launcher find_backward3(int L, int H, int multi) {
+  if (H != 10) return nullptr;
+  switch (L) {
+    case 10: return find_backward3_l10(multi);
+    case 20: return find_backward3_l20(multi);
+    case 64: return find_backward3_l64(multi);
+  }
+  return nullptr;
+}
 }  // namespace gns

@@ -51,6 +51,7 @@ struct ModelDims { int K, L, H, multi; };
 // launch geometry of the warp-specialised backward kernel (gns_backward2.cuh): one grid per CTA at a time
 struct Bwd2Geom {
   bool ok = false;
+  int variant = 2;          // 2: warp-specialised kernel (gns_backward2.cuh), 3: fragment-space kernel (gns_backward3.cuh)
   int PW = 0, CW = 0, T = 0, ctas = 0;
   size_t smem_bytes = 0;
   Act2Layout a2{};
@@ -95,5 +96,8 @@ BwdLauncher find_backward(int L, int H, int multi, int tmax);
 struct Bwd2Args;
 typedef cudaError_t (*Bwd2Launcher)(const Bwd2Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st);
 Bwd2Launcher find_backward2(int L, int H, int multi);
+struct Bwd3Args;
+typedef cudaError_t (*Bwd3Launcher)(const Bwd3Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st);
+Bwd3Launcher find_backward3(int L, int H, int multi);
 
 }  // namespace gns

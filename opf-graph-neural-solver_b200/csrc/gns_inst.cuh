@@ -4,6 +4,7 @@
 #include "gns_forward.cuh"
 #include "gns_backward.cuh"
 #include "gns_backward2.cuh"
+#include "gns_backward3.cuh"
 #include "gns_host.h"
 
 namespace gns {
@@ -81,6 +82,25 @@ static cudaError_t launch_backward2(const Bwd2Args& a, const Bwd2Geom& g, int nu
 template <int L, int H>
 static Bwd2Launcher pick_backward2(int multi) {
   if constexpr (L <= 20) return multi ? launch_backward2<L, H, true> : launch_backward2<L, H, false>;
+  else return nullptr;
+}
+
+template <int L, int H>
+static cudaError_t launch_backward3(const Bwd3Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st) {
+  auto kern = gns_backward3_kernel<L, H, true>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, g.T, g.smem_bytes);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  const int ctas = (int)std::min<long long>(std::min<long long>(a.S, (long long)occ * num_sms), g.ctas);
+  kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
+  return cudaGetLastError();
+}
+template <int L, int H>
+static Bwd3Launcher pick_backward3(int multi) {
+  if constexpr (L <= 20) return multi ? launch_backward3<L, H> : nullptr;
   else return nullptr;
 }
 

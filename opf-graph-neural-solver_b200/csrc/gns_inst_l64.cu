@@ -5,4 +5,5 @@ namespace gns {
 FwdLauncher find_forward_l64(int multi, int VG, int tmax) { return pick_forward<64, 10>(multi, VG, tmax); }
 BwdLauncher find_backward_l64(int multi, int tmax) { return pick_backward<64, 10>(multi, tmax); }
 Bwd2Launcher find_backward2_l64(int multi) { return pick_backward2<64, 10>(multi); }
+Bwd3Launcher find_backward3_l64(int multi) { return pick_backward3<64, 10>(multi); }
 }  // namespace gns

@@ -81,6 +81,8 @@ static SmemPlan plan_smem(int N /* bus slots */, int E, int Gn, int G, int L, in
 int backward_extra_floats(int N, int E, int G, int L, int H, int T);
 // shared memory of the warp-specialised backward kernel, in floats (see gns_backward2.cuh)
 int make_bwd2_smem_floats(int L, int H, int E, int wstep, const Act2Layout& a2);
+int make_bwd3_smem_floats(int L, int H, int N, int E, int wstep, int nwarps, const Act2Layout& a2);
+int frag3_step_floats(int L, int H);
 
 // Warp w runs on SM sub-partition w % 4.  A warp's bus phase costs ~ (1 + c * max lines walked by
 // a lane of its bus group), c ~ 0.2 forward / 0.3 backward (instruction counts).  Groups are placed
@@ -204,7 +206,26 @@ Bwd2Geom choose_bwd2(const gns_plan* plan, const ModelDims& md, long long S) {
   // lost warp-level parallelism.  Kept as the evidence of that experiment and as a second, independent implementation
   // of the adjoint (parity tests run both).
   const int force = env_int("GNS_BWD2", 0);
-  if (force != 1 || S <= 0) return g;
+  if (S <= 0) return g;
+  if (env_int("GNS_BWD3", 0) == 1 && md.multi && md.H == 10 && (md.L == 10 || md.L == 20) && plan->max_walk >= 1) {
+    // fragment-space kernel (gns_backward3.cuh): one thread per bus for the physics, 16-item tiles per warp
+    const int T = std::max(64, ((plan->N + 31) / 32) * 32);
+    const int nw = T / 32;
+    const int nbt = (plan->N + 15) / 16, nlt = (plan->E + 15) / 16;
+    if (T <= 384 && nbt <= 2 * nw && nlt <= 3 * nw && plan->N >= env_int("GNS_BWD2_MIN_SLOTS", 96)) {
+      g.a2 = make_act2_layout(md.L, md.H, plan->N, plan->Ns, plan->E, plan->max_walk);
+      const WLayout W = make_wlayout(md.L, md.H, true);
+      const size_t bytes = (size_t)make_bwd3_smem_floats(md.L, md.H, plan->N, plan->E, W.wstep, nw, g.a2) * 4;
+      if ((int)bytes <= plan->smem_optin) {
+        g.variant = 3; g.PW = nw; g.CW = nw; g.T = T; g.smem_bytes = bytes;
+        const int per_sm = std::max(1, std::min((int)((size_t)233472 / (bytes + 1024)), 65536 / (T * 168)));
+        g.ctas = (int)std::min<long long>(S, (long long)plan->num_sms * per_sm);
+        g.ok = true;
+        return g;
+      }
+    }
+  }
+  if (force != 1) return g;
   if (md.H != 10 || (md.L != 10 && md.L != 20)) return g;           // instantiated dims (latent in registers: L <= 20)
   if (plan->max_walk > 4 || plan->max_walk < 1) return g;            // kB2MaxWalk
   const int min_slots = env_int("GNS_BWD2_MIN_SLOTS", 96);
@@ -315,11 +336,12 @@ Workspace plan_workspace(const gns_plan* plan, const ModelDims& md, long long S,
     // CTA-batches, so the grid count is rounded up to its batch size
     const size_t Sg = (size_t)fwd.nbatch * fwd.G;
     const FragLayout FL = make_frag_layout(md.L, md.H, kFragTile2);
+    const size_t fstep = b2.variant == 3 ? (size_t)frag3_step_floats(md.L, md.H) : (size_t)FL.step;
     w.ckpt = o; o = align(o + Sg * (md.K + 1) * (size_t)b2.a2.state * 4);
     w.pglob = o; o = align(o + Sg * md.K * 4);
     w.act = o; o = align(o + Sg * md.K * (size_t)b2.a2.step * 4);
-    w.gpartial = o; o = align(o + (size_t)b2.ctas * b2.CW * md.K * FL.step * 4);   // one block per consumer warp
-    w.fragsum = o; o = align(o + (size_t)md.K * FL.step * 4);
+    w.gpartial = o; o = align(o + (size_t)b2.ctas * b2.CW * md.K * fstep * 4);   // one block per (consumer) warp
+    w.fragsum = o; o = align(o + (size_t)md.K * fstep * 4);
     w.packed_grad = o; o = align(o + (size_t)md.K * W.wstep * 4);
   } else if (need_grad) {
     const size_t nst = (size_t)(4 + md.L) * row_stride(plan->Ns * fwd.G);
@@ -466,6 +488,27 @@ extern "C" int gns_plan_create(int n_bus, int n_line, int n_gen, const int32_t* 
       blk[p->to.tr + e] = (uint16_t)p->bus_rank[t_bus[e]];
     }
     for (int r = 0; r < n_bus; ++r) blk[p->to.ext_rank + r] = (uint16_t)p->bus_order[r];
+    // lines as items: per activation column (in_pos) the walking slot, walk position, receiving bus rank, line id;
+    // and per bus rank the columns of its in-lines (in_ids is already grouped by bus in rank order, ascending line id)
+    for (int s = 0; s < Ns; ++s)
+      for (int e = p->slot_in_begin[s]; e < p->slot_in_end[s]; ++e) {
+        const int c = blk[p->to.in_pos + e];
+        blk[p->to.col_slot + c] = (uint16_t)s;
+        blk[p->to.col_it + c] = (uint16_t)(e - p->slot_in_begin[s]);
+        blk[p->to.col_brank + c] = (uint16_t)p->bus_rank[p->slot_bus[s]];
+        blk[p->to.col_line + c] = blk[p->to.in_ids + e];
+      }
+    {
+      int off = 0;
+      for (int r = 0; r < n_bus; ++r) {
+        const int b = p->bus_order[r];
+        blk[p->to.rin_b + r] = (uint16_t)off;
+        const int ps = prim_slot_of_bus[b];
+        const int e0 = p->slot_in_begin[ps], e1 = e0 + (p->in_rowptr[b + 1] - p->in_rowptr[b]);
+        for (int e = e0; e < e1; ++e) blk[p->to.rin_cols + off++] = blk[p->to.in_pos + e];
+      }
+      blk[p->to.rin_b + n_bus] = (uint16_t)off;
+    }
   }
   std::vector<float> expect(2 * n_line + n_gen);
   for (int e = 0; e < n_line; ++e) { expect[e] = (float)(f_bus[e] + 1); expect[n_line + e] = (float)(t_bus[e] + 1); }
