@@ -144,7 +144,8 @@ int gns_layout_export(const char* name, int K, int latent_dim, int hidden_dim, i
 /* Launch geometry chosen for this plan/model (for bench/roofline reporting; nothing in the reference corresponds):
  * out[0]=grids per CTA, out[1]=threads per CTA, out[2]=dynamic smem bytes, out[3]=CTAs launched for S grids
  * (persistent kernels: min(batches, SMs x resident CTAs)), out[4]=items per thread (grids, or bus slots in the
- * warp-specialised backward kernel), out[5]=CTA batches, out[6]=SMs, out[7]=launch-bounds variant. */
+ * warp-specialised backward kernel) or bus items per warp (fragment-space backward kernel), out[5]=CTA batches,
+ * out[6]=SMs, out[7]=launch-bounds variant. */
 int gns_launch_info(const gns_plan* plan, int64_t S, int K, int latent_dim, int hidden_dim,
                     int multiple_phi, int backward, int32_t out[8]);
 

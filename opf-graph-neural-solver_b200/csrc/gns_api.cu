@@ -203,8 +203,9 @@ extern "C" int gns_launch_info(const gns_plan* plan, int64_t S, int K, int L, in
   if (backward) {
     const Bwd2Geom b2 = choose_bwd2(plan, md, S);
     if (b2.ok) {   // warp-specialised kernel: one grid per CTA at a time
-      out[0] = 1; out[1] = b2.T; out[2] = (int32_t)b2.smem_bytes; out[3] = b2.ctas; out[4] = 2;
-      out[5] = (int32_t)std::min<int64_t>(S, 2147483647); out[6] = plan->num_sms; out[7] = 384;
+      out[0] = 1; out[1] = b2.T; out[2] = (int32_t)b2.smem_bytes; out[3] = b2.ctas; out[4] = b2.variant == 3 ? 16 * b2.bt : 2;
+      out[5] = (int32_t)std::min<int64_t>(S, 2147483647); out[6] = plan->num_sms;
+      out[7] = b2.variant == 3 ? (b2.bt == 2 ? 320 : (b2.T <= 256 ? 256 : 640)) : 384;
       return 0;
     }
   }

@@ -270,7 +270,7 @@ static int run_backward3(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2
   const int32_t* d_inv = get_frag_map(plan, md, 3);
   if (!d_inv) return -2;
   const int nw = b2.T / 32;
-  const int nparts = b2.ctas * nw;
+  const int nparts = b2.ctas * b2.parts_per_cta;
   float* gacc = reinterpret_cast<float*>(wsb + ws.gpartial);
   cudaError_t e = cudaMemsetAsync(gacc, 0, (size_t)nparts * per_part * 4, st);
   if (e != cudaSuccess) { set_error(std::string("memset gacc: ") + cudaGetErrorString(e)); return -2; }
@@ -284,6 +284,7 @@ static int run_backward3(gns_plan* plan, const ModelDims& md, const Bwd2Geom& b2
   a.act = reinterpret_cast<const float*>(wsb + ws.act);
   a.grad_total = grad_total; a.grad_last = grad_last; a.grad_v = grad_v; a.grad_theta = grad_theta;
   a.gacc = gacc;
+  a.acc_shared = b2.parts_per_cta == 1 ? 1 : 0;
   a.topo = plan->d_topo;
   a.S = S; a.N = plan->N; a.Ns = plan->Ns; a.E = plan->E; a.Gn = plan->Gn; a.K = md.K;
   a.a2 = b2.a2;

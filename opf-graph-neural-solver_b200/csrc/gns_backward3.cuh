@@ -54,7 +54,7 @@ struct Bwd3Smem {          // offsets in floats
   int mbar;
   int total;
 };
-constexpr int kB3Scr = 16 * 24 + 2 * 16 * 10;     // adj state tile [16][24] + two hidden tiles [16][10]
+constexpr int kB3Scr = 16 * 24;     // adjoint-state tile [16][24]; later in the same tile: two hidden tiles [16][10]
 
 struct Bwd3Topo { int fa, ta, fr, tr, in_ids, in_pos, out_ids, col_slot, col_it, col_brank, rin_cols, rin_b; int total; };
 __host__ __device__ inline Bwd3Topo make_bwd3_topo(int N, int E) {
@@ -98,7 +98,7 @@ __host__ __device__ inline Bwd3Smem make_bwd3_smem(int L, int H, int N, int E, i
     s.adjA = u; s.d1l = u + NbP * H;
   }
   s.scratch = take(nwarps * kB3Scr);
-  s.red = take(2 * 64);
+  s.red = take(2 * 4 * 32);
   s.topo = take((make_bwd3_topo(N, E).total + 1) / 2);
   s.mbar = take(2 * 8);
   s.total = o;
@@ -130,7 +130,8 @@ struct Bwd3Args {
   const float* buses; const float* lines; const float* gens;
   const float* ck2; const float* pglob; const float* act;
   const float* grad_total; const float* grad_last; const float* grad_v; const float* grad_theta;
-  float* gacc;              // [ctas * nwarps][K][FragLayout3.step]
+  float* gacc;              // [ctas * nwarps][K][FragLayout3.step]  (acc_shared: [ctas][K][step], the warps' reductions race)
+  int acc_shared;
   const uint16_t* topo;
   long long S;
   int N, Ns, E, Gn, K;
@@ -144,11 +145,18 @@ struct Bwd3Args {
 __device__ __forceinline__ uint32_t tf32_small(float x) {
   return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
 }
+// mma.sync without `volatile`: the products of a tile are pure data flow, so ptxas may interleave the independent
+// accumulator chains of neighbouring calls (a chain of dependent HMMAs waits ~20 cycles per link)
+__device__ __forceinline__ void mma_nv(float (&d)[4], const uint32_t (&a)[4], float b0, float b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
 // c += A (big / small quads) x B (big / small pairs), 3-term TF32
 __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], float2 bb, float2 bs) {
-  mma_tf32(c, as, __float_as_uint(bb.x), __float_as_uint(bb.y));
-  mma_tf32(c, ab, __float_as_uint(bb.x), __float_as_uint(bb.y));
-  mma_tf32(c, ab, __float_as_uint(bs.x), __float_as_uint(bs.y));
+  mma_nv(c, as, bb.x, bb.y);
+  mma_nv(c, ab, bb.x, bb.y);
+  mma_nv(c, ab, bs.x, bs.y);
 }
 // accumulator fragment (rows g, g+8; columns col, col+1) -> A quad of the k step that covers these columns,
 // each element multiplied by the LeakyReLU slope of its (item, column) bit
@@ -175,19 +183,26 @@ template <int KS, int NT, int HP>
 __device__ __forceinline__ void mma_rows(float (&c)[NT][4], const uint32_t (&ab)[KS][4], const uint32_t (&as)[KS][4],
                                          const float* wbig, const float* wsmall, int row0, int nrows, int colshift, int g, int t) {
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int r = 8 * nt + g - colshift;
-    const bool rv = r >= 0 && r < nrows;
-    const int off = (row0 + (rv ? r : 0)) * HP + 2 * t;
+  for (int ks = 0; ks < KS; ++ks) {
+    float2 bb[NT], bs[NT];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      float2 bb = make_float2(0.f, 0.f), bs = bb;
+    for (int nt = 0; nt < NT; ++nt) {
+      const int r = 8 * nt + g - colshift;
+      const bool rv = r >= 0 && r < nrows;
+      const int off = (row0 + (rv ? r : 0)) * HP + 2 * t;
+      bb[nt] = make_float2(0.f, 0.f); bs[nt] = bb[nt];
       if (rv && 8 * ks + 2 * t < HP) {
-        bb = *reinterpret_cast<const float2*>(wbig + off + 8 * ks);
-        bs = *reinterpret_cast<const float2*>(wsmall + off + 8 * ks);
+        bb[nt] = *reinterpret_cast<const float2*>(wbig + off + 8 * ks);
+        bs[nt] = *reinterpret_cast<const float2*>(wsmall + off + 8 * ks);
       }
-      mma3(c[nt], ab[ks], as[ks], bb, bs);
     }
+    // term-major: consecutive HMMAs go to different accumulators
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) mma_nv(c[nt], as[ks], bb[nt].x, bb[nt].y);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) mma_nv(c[nt], ab[ks], bb[nt].x, bb[nt].y);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) mma_nv(c[nt], ab[ks], bs[nt].x, bs[nt].y);
   }
 }
 
@@ -215,17 +230,27 @@ __device__ __forceinline__ void dw_chunk(float (&acc)[(R + 7) / 8][4], const flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) as[st][i] = tf32_small(__uint_as_float(ab[st][i]));
   }
+  float4 b[NT], bs[NT];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int r = nt * 8 + g;
     const float* rp = (((nt * 8 + 8 <= R) || (r < R)) ? row(r) : zrow) + 4 * t;
-    const float4 b = *reinterpret_cast<const float4*>(rp);
-    const float2 bb0 = make_float2(b.x, b.y), bb1 = make_float2(b.z, b.w);
-    const float2 bs0 = make_float2(__uint_as_float(tf32_small(b.x)), __uint_as_float(tf32_small(b.y)));
-    const float2 bs1 = make_float2(__uint_as_float(tf32_small(b.z)), __uint_as_float(tf32_small(b.w)));
-    mma3(acc[nt], ab[0], as[0], bb0, bs0);
-    mma3(acc[nt], ab[1], as[1], bb1, bs1);
+    b[nt] = *reinterpret_cast<const float4*>(rp);
+    bs[nt] = make_float4(__uint_as_float(tf32_small(b[nt].x)), __uint_as_float(tf32_small(b[nt].y)),
+                         __uint_as_float(tf32_small(b[nt].z)), __uint_as_float(tf32_small(b[nt].w)));
   }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) mma_nv(acc[nt], as[0], b[nt].x, b[nt].y);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) mma_nv(acc[nt], ab[0], b[nt].x, b[nt].y);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) mma_nv(acc[nt], ab[0], bs[nt].x, bs[nt].y);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) mma_nv(acc[nt], as[1], b[nt].z, b[nt].w);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) mma_nv(acc[nt], ab[1], b[nt].z, b[nt].w);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) mma_nv(acc[nt], ab[1], bs[nt].z, bs[nt].w);
 }
 template <int NT>
 __device__ __forceinline__ void dw_flush(float (&acc)[NT][4], float* __restrict__ gfrag) {
@@ -240,9 +265,11 @@ __device__ __forceinline__ void dw_flush(float (&acc)[NT][4], float* __restrict_
     for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
 }
 
-template <int L, int H, bool MULTI>
-__global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a) {
-  static_assert(MULTI && H == 10 && (L == 10 || L == 20), "instantiated for multiple phi, hidden 10, latent 10 / 20");
+// BT / LT: bus / line tiles per warp (the host picks the warp count so that they suffice); TB, MINB: launch bounds
+template <int L, int H, int BT, int LT, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) gns_backward3_kernel(const Bwd3Args a) {
+  static_assert(H == 10 && (L == 10 || L == 20), "instantiated for multiple phi, hidden 10, latent 10 / 20");
+  constexpr bool MULTI = true;
   constexpr WLayout W = make_wlayout(L, H, MULTI);
   constexpr FragLayout FL = make_frag_layout3(L, H);
   constexpr int HP = pad4(H);
@@ -280,8 +307,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
   float* const s_adjA = smem + a.sm.adjA;
   float* const s_d1l = smem + a.sm.d1l;
   float* const scr = smem + a.sm.scratch + warp * kB3Scr;
-  float* const scr_st = scr;                            // [16][SW]
-  float* const scr_h0 = scr + 16 * SW;                  // [16][H]
+  float* const scr_st = scr;                            // [16][SW]   (dead once the output-layer gradient is done)
+  float* const scr_h0 = scr;                            // [16][H]
   float* const scr_h1 = scr_h0 + 16 * H;                // [16][H]
   float* const s_red = smem + a.sm.red;
   uint16_t* const s_topo = reinterpret_cast<uint16_t*>(smem + a.sm.topo);
@@ -339,9 +366,9 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
   }
   // ---- tiles of this warp: bus tiles w, w + nwarps; line tiles w, w + nwarps, ... ----
   const int nbt = (N + 15) / 16, nlt = (E + 15) / 16;
-  int ps_lo[2], ps_hi[2];                 // primary slots of this lane's items (g, g+8) in its two bus tiles: slope-word columns
+  int ps_lo[BT], ps_hi[BT];               // primary slots of this lane's items (g, g+8) in its bus tiles: slope-word columns
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < BT; ++j) {
     const int rlo = (warp + j * nwarps) * 16 + g, rhi = rlo + 8;
     ps_lo[j] = rlo < N ? (int)a.topo[a.to.rank_of + (int)a.topo[a.to.ext_rank + rlo]] : -1;
     ps_hi[j] = rhi < N ? (int)a.topo[a.to.rank_of + (int)a.topo[a.to.ext_rank + rhi]] : -1;
@@ -349,10 +376,10 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
   int red_parity = 0;
   uint32_t ph_state = 0, ph_nxt = 0, ph_w = 0, ph_act = 0;
   int nxt_buf = 0;
-  float* const gacc_w = a.gacc + ((size_t)blockIdx.x * nwarps + warp) * ((size_t)K * FL.step);
+  float* const gacc_w = a.gacc + (a.acc_shared ? (size_t)blockIdx.x : (size_t)blockIdx.x * nwarps + warp) * ((size_t)K * FL.step);
 
   auto block_sum = [&](float (&x)[3], int nv) {          // deterministic sum over the CTA (barrier inside)
-    float* buf = s_red + red_parity * 64;
+    float* buf = s_red + red_parity * 128;
     red_parity ^= 1;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
@@ -404,7 +431,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
 
   // adjoint of the latent (and this step's additions to adj v, theta, dP, dQ in columns 0..3) of this warp's two bus
   // tiles, as accumulator fragments: columns 8 nt + 2t, +1 of items g, g+8
-  float ast[2][SNT][4];
+  float ast[BT][SNT][4];
 
   for (long long grid = first_grid; grid < a.S; grid += grid_step) {
     // ---------------- per-grid constants ----------------
@@ -441,7 +468,7 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
       for (int c = 0; c < 5; ++c) s_featp[c * EP + col] = __ldg(lr + c);
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < BT; ++j)
 #pragma unroll
       for (int nt = 0; nt < SNT; ++nt)
 #pragma unroll
@@ -451,10 +478,6 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
     float pglob = __ldg(a.pglob + (size_t)grid * K + (K - 1));
 
     for (int k = K - 1; k >= 0; --k) {
-      const float* const act_k = a.act + ((size_t)grid * K + k) * (size_t)a.a2.step;
-      const uint32_t* const mask_k[3] = {reinterpret_cast<const uint32_t*>(act_k + a.a2.mask[0]),
-                                         reinterpret_cast<const uint32_t*>(act_k + a.a2.mask[1]),
-                                         reinterpret_cast<const uint32_t*>(act_k + a.a2.mask[2])};
       if (tid == 0) {
         if (k >= 1) issue_nxt(grid, k, nxt_buf ^ 1);
         else if (grid + grid_step < a.S) issue_nxt(grid + grid_step, K, nxt_buf ^ 1);
@@ -546,6 +569,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
         for (int e = e_in0; e < e_in1; ++e) { const int l = t_ini[e]; if (l < N) adjth -= s_adjD[l]; }
         s_gout[0 * NbP + r_me] = is_gen ? 0.f : adjv;
         s_gout[1 * NbP + r_me] = adjth;
+        s_adj4[0 * NbP + r_me] = adjv;      // the step's MLP additions arrive at the end of the step
+        s_adj4[1 * NbP + r_me] = adjth;
       }
       // ---------------- weights of this step: wait, split once ----------------
       mbar_wait(s_bar + BAR_W, ph_w);
@@ -568,118 +593,81 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
         const float* const wmfs = s_ws + W.off_mf[0] + q * W.mf_size;
         float* const gln = gk + q * FL.net;
         float* const gphi = gk + q * FL.net;
-        const uint32_t* const mrow = mask_k[q];
+        // slope words of this lane's items (bus tiles: bits 0..9 h1L, 10..19 h2L; line tiles: h1, h2 of the phi net):
+        // fetched here, first used after the activation blocks have landed
+        uint32_t mw[BT][2], lw[LT][2];
+        {
+          const uint32_t* const mrow =
+              reinterpret_cast<const uint32_t*>(a.act + ((size_t)grid * K + k) * (size_t)a.a2.step + a.a2.mask[q]);
+#pragma unroll
+          for (int j = 0; j < BT; ++j) {
+            mw[j][0] = ps_lo[j] >= 0 ? __ldg(mrow + ps_lo[j]) : 0u;
+            mw[j][1] = ps_hi[j] >= 0 ? __ldg(mrow + ps_hi[j]) : 0u;
+          }
+          const uint32_t* const lmask = mrow + a.a2.NsM;          // row 1 + it
+#pragma unroll
+          for (int j = 0; j < LT; ++j) {
+            const int clo = (warp + j * nwarps) * 16 + g, chi = clo + 8;
+            lw[j][0] = clo < E ? __ldg(lmask + (int)t_cit[clo] * a.a2.NsM + (int)t_cslot[clo]) : 0u;
+            lw[j][1] = chi < E ? __ldg(lmask + (int)t_cit[chi] * a.a2.NsM + (int)t_cslot[chi]) : 0u;
+          }
+        }
         mbar_wait(s_bar + BAR_ACT, ph_act & 1u);
         ph_act ^= 1u;
 
         // ======== phase A: L net of the pair on this warp's bus tiles ========
-        float accOutM[2][2][4];                 // m net output layer (adjoint state x [h2 | 1])
-        constexpr int NTW1 = (4 + L + H + 2 + 7) / 8;
-        float accOutS[1][4], accW2[2][4], accW1[NTW1][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          accOutS[0][i] = 0.f;
-#pragma unroll
-          for (int x = 0; x < 2; ++x) { accW2[x][i] = 0.f; accOutM[0][x][i] = 0.f; accOutM[1][x][i] = 0.f; }
-#pragma unroll
-          for (int x = 0; x < NTW1; ++x) accW1[x][i] = 0.f;
-        }
-        // slope words of the L net (bits 0..9: h1L, 10..19: h2L) of this lane's items, fetched up front
-        uint32_t mw[2][2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          mw[j][0] = ps_lo[j] >= 0 ? __ldg(mrow + ps_lo[j]) : 0u;
-          mw[j][1] = ps_hi[j] >= 0 ? __ldg(mrow + ps_hi[j]) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < BT; ++j) {
           const int tile = warp + j * nwarps;
           if (tile < nbt) {
             const int i0 = tile * 16;                        // first bus rank of the tile
             const int rlo = i0 + g, rhi = i0 + g + 8;
             const uint32_t wlo = mw[j][0], whi = mw[j][1];
-            // ---- output layer: dh2 = g_out x Wout ----
+            // ---- output layer: dh2 = g_out x Wout, and its weight gradient ----
             float c2[2][4];
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) c2[nt][i] = 0.f;
-            uint32_t ab[SNT][4], as[SNT][4];
             float qd[4];
             if (q == 2) {
-              // adjoint state tile -> item-major scratch (hidden-side operand of the output-layer gradient) and A quads
-              __syncwarp();
 #pragma unroll
-              for (int nt = 0; nt < SNT; ++nt) {
-                frag_to_quad(ast[j][nt], 0u, 0u, 8 * nt + 2 * t, 0, false, ab[nt], as[nt], qd);
-                store_quad(scr_st, SW, g, 8 * nt + 2 * t, qd);
-              }
-              // dh2[item][o] = sum_r' ast[item][r'] Wout[r' - 4][o]: B(k = r', n = o) = wln[ln_wo + (r' - 4) HP + o]
+              for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-              for (int nt = 0; nt < 2; ++nt) {
-                const int o = 8 * nt + g;
+                for (int i = 0; i < 4; ++i) c2[nt][i] = 0.f;
+              {
+                // adjoint state tile -> item-major scratch (hidden-side operand of the output-layer gradient) and A quads
+                uint32_t ab[SNT][4], as[SNT][4];
+                __syncwarp();
+#pragma unroll
+                for (int nt = 0; nt < SNT; ++nt) {
+                  frag_to_quad(ast[j][nt], 0u, 0u, 8 * nt + 2 * t, 0, false, ab[nt], as[nt], qd);
+                  store_quad(scr_st, SW, g, 8 * nt + 2 * t, qd);
+                }
+                // dh2[item][o] = sum_r' ast[item][r'] Wout[r' - 4][o]: B(k = r', n = o) = wln[ln_wo + (r' - 4) HP + o]
 #pragma unroll
                 for (int ks = 0; ks < SNT; ++ks) {
-                  const int r0 = 8 * ks + 2 * t - 4;      // weight rows of k slots t, t+4
-                  float2 bb = make_float2(0.f, 0.f), bs = bb;
-                  if (o < HP) {
-                    if (r0 >= 0 && r0 < L) { bb.x = wln[W.ln_wo + r0 * HP + o]; bs.x = wlns[W.ln_wo + r0 * HP + o]; }
-                    if (r0 + 1 >= 0 && r0 + 1 < L) { bb.y = wln[W.ln_wo + (r0 + 1) * HP + o]; bs.y = wlns[W.ln_wo + (r0 + 1) * HP + o]; }
+                  float2 bb[2], bs[2];
+#pragma unroll
+                  for (int nt = 0; nt < 2; ++nt) {
+                    const int o = 8 * nt + g;
+                    const int r0 = 8 * ks + 2 * t - 4;      // weight rows of k slots t, t+4
+                    bb[nt] = make_float2(0.f, 0.f); bs[nt] = bb[nt];
+                    if (o < HP) {
+                      if (r0 >= 0 && r0 < L) { bb[nt].x = wln[W.ln_wo + r0 * HP + o]; bs[nt].x = wlns[W.ln_wo + r0 * HP + o]; }
+                      if (r0 + 1 >= 0 && r0 + 1 < L) { bb[nt].y = wln[W.ln_wo + (r0 + 1) * HP + o]; bs[nt].y = wlns[W.ln_wo + (r0 + 1) * HP + o]; }
+                    }
                   }
-                  mma3(c2[nt], ab[ks], as[ks], bb, bs);
+#pragma unroll
+                  for (int nt = 0; nt < 2; ++nt) mma_nv(c2[nt], as[ks], bb[nt].x, bb[nt].y);
+#pragma unroll
+                  for (int nt = 0; nt < 2; ++nt) mma_nv(c2[nt], ab[ks], bb[nt].x, bb[nt].y);
+#pragma unroll
+                  for (int nt = 0; nt < 2; ++nt) mma_nv(c2[nt], ab[ks], bs[nt].x, bs[nt].y);
                 }
               }
-            } else {
-              // scalar net: outer product of the output adjoint with the output row
-              const float glo = s_gout[q * NbP + rlo], ghi = s_gout[q * NbP + rhi];
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) {
-                const int o = 8 * nt + 2 * t;
-                const float w0 = o < HP ? wln[W.ln_wo + o] : 0.f, w1 = o + 1 < HP ? wln[W.ln_wo + o + 1] : 0.f;
-                c2[nt][0] = glo * w0; c2[nt][1] = glo * w1; c2[nt][2] = ghi * w0; c2[nt][3] = ghi * w1;
-              }
-            }
-            // ---- d2 = dh2 * slope(h2L); its item-major copy is the hidden-side operand of dW2 ----
-            uint32_t db[2][4], ds[2][4];
-            __syncwarp();
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              frag_to_quad(c2[nt], wlo, whi, 8 * nt + 2 * t, H, 8 * nt + 2 * t < H, db[nt], ds[nt], qd);
-              if (8 * nt + 2 * t < H) store_quad(scr_h0, H, g, 8 * nt + 2 * t, qd);
-            }
-            // ---- second layer: d1 = (d2 x W2) * slope(h1L) ----
-            float c1[2][4];
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) c1[nt][i] = 0.f;
-            mma_rows<2, 2, HP>(c1, db, ds, wln + W.ln_w2, wlns + W.ln_w2, 0, H, 0, g, t);
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              frag_to_quad(c1[nt], wlo, whi, 8 * nt + 2 * t, 0, 8 * nt + 2 * t < H, db[nt], ds[nt], qd);
-              if (8 * nt + 2 * t < H) store_quad(scr_h1, H, g, 8 * nt + 2 * t, qd);
-            }
-            // ---- first layer dX: adjoint state (+= d1 x W1[:4+L]) and adjoint of the aggregate (d1 x M) ----
-            mma_rows<2, SNT, HP>(ast[j], db, ds, wln + W.ln_w1, wlns + W.ln_w1, 0, SC, 0, g, t);
-            float cA[2][4];
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) cA[nt][i] = 0.f;
-            mma_rows<2, 2, HP>(cA, db, ds, wmf, wmfs, 0, H, 0, g, t);
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const int col = 8 * nt + 2 * t;
-              if (col < H) {
-                *reinterpret_cast<float2*>(s_adjA + (i0 + g) * H + col) = make_float2(cA[nt][0], cA[nt][1]);
-                *reinterpret_cast<float2*>(s_adjA + (i0 + g + 8) * H + col) = make_float2(cA[nt][2], cA[nt][3]);
-              }
-            }
-            __syncwarp();
-            // ---- weight gradients of the L net on this tile (one k16 chunk each) ----
-            if (q == 2) {
+              __syncwarp();
               // dWout[i][j] += adjm'[i] h2[j], dbout[i] += adjm'[i]: A = adjoint state tile (columns 2g, 2g+1 of 16 per
               // M tile), B = [h2L | 1] item-major (two scalar loads per k step)
+              float accOutM[2][2][4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { accOutM[0][0][i] = 0.f; accOutM[0][1][i] = 0.f; accOutM[1][0][i] = 0.f; accOutM[1][1][i] = 0.f; }
 #pragma unroll
               for (int st = 0; st < 2; ++st) {
                 const int it0 = 4 * t + 2 * st;
@@ -708,31 +696,98 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
                   for (int mt = 0; mt < 2; ++mt) mma3(accOutM[mt][nt], ab2[mt], as2[mt], bb, bs);
                 }
               }
-            } else {
-              dw_chunk<H + 1, 1>(accOutS, s_h2L + i0 * H, H, [&](int) { return s_gout + q * NbP + i0; }, s_zrow + i0, s_ones_b + i0);
-            }
-            dw_chunk<H, H + 1>(accW2, scr_h0, H, [&](int r) { return (r < H ? s_h1L + r * NbP : s_ones_b) + i0; }, s_zrow + i0, nullptr);
-            dw_chunk<H, 4 + L + H + 2>(accW1, scr_h1, H,
-                                       [&](int r) {
-                                         return (r < 4 + L ? s_state + r * NbP
-                                                           : (r < 4 + L + H ? s_A + (r - 4 - L) * NbP : (r == 4 + L + H ? s_deg : s_ones_b))) + i0;
-                                       },
-                                       s_zrow + i0, nullptr);
-          }
-        }
-        // flush the L net's accumulators of this warp
-        if (q == 2) {
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+                  red_add_v4(gln + FL.out + ((mt * 2 + nt) * 32 + lane) * 4, accOutM[mt][nt][0], accOutM[mt][nt][1], accOutM[mt][nt][2],
+                             accOutM[mt][nt][3]);
+            } else {
+              // scalar net: outer product of the output adjoint with the output row
+              const float glo = s_gout[q * NbP + rlo], ghi = s_gout[q * NbP + rhi];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                const int o = 8 * nt + 2 * t;
+                const float w0 = o < HP ? wln[W.ln_wo + o] : 0.f, w1 = o + 1 < HP ? wln[W.ln_wo + o + 1] : 0.f;
+                c2[nt][0] = glo * w0; c2[nt][1] = glo * w1; c2[nt][2] = ghi * w0; c2[nt][3] = ghi * w1;
+              }
+              float accOutS[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+              dw_chunk<H + 1, 1>(accOutS, s_h2L + i0 * H, H, [&](int) { return s_gout + q * NbP + i0; }, s_zrow + i0, s_ones_b + i0);
+              dw_flush<1>(accOutS, gln + FL.out);
+            }
+            // ---- d2 = dh2 * slope(h2L); its item-major copy is the hidden-side operand of dW2 ----
+            uint32_t db[2][4], ds[2][4];
+            __syncwarp();              // the adjoint-state tile in the scratch is dead: the hidden tiles take its place
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              frag_to_quad(c2[nt], wlo, whi, 8 * nt + 2 * t, H, 8 * nt + 2 * t < H, db[nt], ds[nt], qd);
+              if (8 * nt + 2 * t < H) store_quad(scr_h0, H, g, 8 * nt + 2 * t, qd);
+            }
+            // ---- second layer: d1 = (d2 x W2) * slope(h1L) ----
+            float c1[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
-              red_add_v4(gln + FL.out + ((mt * 2 + nt) * 32 + lane) * 4, accOutM[mt][nt][0], accOutM[mt][nt][1], accOutM[mt][nt][2],
-                         accOutM[mt][nt][3]);
-        } else {
-          dw_flush<1>(accOutS, gln + FL.out);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) c1[nt][i] = 0.f;
+            mma_rows<2, 2, HP>(c1, db, ds, wln + W.ln_w2, wlns + W.ln_w2, 0, H, 0, g, t);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              frag_to_quad(c1[nt], wlo, whi, 8 * nt + 2 * t, 0, 8 * nt + 2 * t < H, db[nt], ds[nt], qd);
+              if (8 * nt + 2 * t < H) store_quad(scr_h1, H, g, 8 * nt + 2 * t, qd);
+            }
+            // ---- first layer dX: adjoint state (+= d1 x W1[:4+L]) and adjoint of the aggregate (d1 x M) ----
+            mma_rows<2, SNT, HP>(ast[j], db, ds, wln + W.ln_w1, wlns + W.ln_w1, 0, SC, 0, g, t);
+            {
+              float cA[2][4];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cA[nt][i] = 0.f;
+              mma_rows<2, 2, HP>(cA, db, ds, wmf, wmfs, 0, H, 0, g, t);
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                const int col = 8 * nt + 2 * t;
+                if (col < H) {
+                  *reinterpret_cast<float2*>(s_adjA + (i0 + g) * H + col) = make_float2(cA[nt][0], cA[nt][1]);
+                  *reinterpret_cast<float2*>(s_adjA + (i0 + g + 8) * H + col) = make_float2(cA[nt][2], cA[nt][3]);
+                }
+              }
+            }
+            __syncwarp();
+            // ---- weight gradients of the hidden layers on this tile (one k16 chunk each), flushed per tile ----
+            {
+              float accW2[2][4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { accW2[0][i] = 0.f; accW2[1][i] = 0.f; }
+              dw_chunk<H, H + 1>(accW2, scr_h0, H, [&](int r) { return (r < H ? s_h1L + r * NbP : s_ones_b) + i0; }, s_zrow + i0, nullptr);
+              dw_flush<2>(accW2, gln + FL.w2);
+            }
+            {
+              // W1 rows: 4 + L state columns | H aggregate columns | degree | 1, in two calls to bound the live registers
+              constexpr int RW1 = 4 + L + H + 2;
+              constexpr int R0 = RW1 > 24 ? 24 : 16;       // first call: whole n tiles
+              auto w1row = [&](int r) {
+                return (r < 4 + L ? s_state + r * NbP
+                                  : (r < 4 + L + H ? s_A + (r - 4 - L) * NbP : (r == 4 + L + H ? s_deg : s_ones_b))) + i0;
+              };
+              float acc0[R0 / 8][4];
+#pragma unroll
+              for (int x = 0; x < R0 / 8; ++x)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc0[x][i] = 0.f;
+              dw_chunk<H, R0>(acc0, scr_h1, H, w1row, s_zrow + i0, nullptr);
+              dw_flush<R0 / 8>(acc0, gln + FL.w1);
+              constexpr int R1 = RW1 - R0;
+              float acc1[(R1 + 7) / 8][4];
+#pragma unroll
+              for (int x = 0; x < (R1 + 7) / 8; ++x)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc1[x][i] = 0.f;
+              dw_chunk<H, R1>(acc1, scr_h1, H, [&](int r) { return w1row(r + R0); }, s_zrow + i0, nullptr);
+              dw_flush<(R1 + 7) / 8>(acc1, gln + FL.w1 + (R0 / 8) * kFragTile2);
+            }
+          }
         }
-        dw_flush<2>(accW2, gln + FL.w2);
-        dw_flush<NTW1>(accW1, gln + FL.w1);
         mbar_wait(s_bar + BAR_ACT + 1, (ph_act >> 1) & 1u);     // (ph_act bit 0 was flipped above; bit 1 tracks the line block)
         __syncthreads();                       // adjA complete; everyone is done with h2L / h1L / A of this pair
         ph_act ^= 2u;
@@ -746,16 +801,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
         float accW2l[2][4], accW1f[1][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { accW2l[0][i] = 0.f; accW2l[1][i] = 0.f; accW1f[0][i] = 0.f; }
-        const uint32_t* const lmask = mrow + a.a2.NsM;          // row 1 + it
-        uint32_t lw[3][2];                                       // slope words of this lane's lines, fetched up front
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int clo = (warp + j * nwarps) * 16 + g, chi = clo + 8;
-          lw[j][0] = clo < E ? __ldg(lmask + (int)t_cit[clo] * a.a2.NsM + (int)t_cslot[clo]) : 0u;
-          lw[j][1] = chi < E ? __ldg(lmask + (int)t_cit[chi] * a.a2.NsM + (int)t_cslot[chi]) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < LT; ++j) {
           const int tile = warp + j * nwarps;
           if (tile >= nlt) break;
           const int c0 = tile * 16;
@@ -805,13 +852,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
         }
 
         // ======== phase D: adjP per bus (gather over its in-lines), adj m += adjP x W1m, dW1m ========
-        float accW1m[(L + 1 + 7) / 8][4];
 #pragma unroll
-        for (int x = 0; x < (L + 1 + 7) / 8; ++x)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) accW1m[x][i] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < BT; ++j) {
           const int tile = warp + j * nwarps;
           if (tile < nbt) {
             const int i0 = tile * 16;
@@ -841,16 +883,21 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
             // adjoint state columns 4.. += adjP x W1m
             mma_rows<2, SNT, HP>(ast[j], db, ds, wphi + W.phi_w1m, wphis + W.phi_w1m, 0, L, 4, g, t);
             __syncwarp();
+            float accW1m[(L + 1 + 7) / 8][4];
+#pragma unroll
+            for (int x = 0; x < (L + 1 + 7) / 8; ++x)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) accW1m[x][i] = 0.f;
             dw_chunk<H, L + 1>(accW1m, scr_h0, H, [&](int r) { return (r < L ? s_state + (4 + r) * NbP : s_ones_b) + i0; }, s_zrow + i0,
                                nullptr);
+            dw_flush<(L + 1 + 7) / 8>(accW1m, gphi + FL.w1m);
           }
         }
-        dw_flush<(L + 1 + 7) / 8>(accW1m, gphi + FL.w1m);
       }  // pairs
 
       // ---------------- this step's additions to adj (v, theta, dP, dQ): fragments -> rows; then per bus ----------------
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < BT; ++j) {
         const int tile = warp + j * nwarps;
         if (tile < nbt && t < 2) {
           const int i0 = tile * 16;
@@ -861,8 +908,8 @@ __global__ void __launch_bounds__(384, 1) gns_backward3_kernel(const Bwd3Args a)
       }
       __syncthreads();
       if (bus_on) {
-        s_adj4[0 * NbP + r_me] = adjv + s_a4[0 * NbP + r_me];
-        s_adj4[1 * NbP + r_me] = adjth + s_a4[1 * NbP + r_me];
+        s_adj4[0 * NbP + r_me] += s_a4[0 * NbP + r_me];
+        s_adj4[1 * NbP + r_me] += s_a4[1 * NbP + r_me];
         s_adj4[2 * NbP + r_me] = s_a4[2 * NbP + r_me];
         s_adj4[3 * NbP + r_me] = s_a4[3 * NbP + r_me];
       }

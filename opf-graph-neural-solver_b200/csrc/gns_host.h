@@ -53,6 +53,8 @@ struct Bwd2Geom {
   bool ok = false;
   int variant = 2;          // 2: warp-specialised kernel (gns_backward2.cuh), 3: fragment-space kernel (gns_backward3.cuh)
   int PW = 0, CW = 0, T = 0, ctas = 0;
+  int bt = 0, lt = 0;       // variant 3: bus / line tiles per warp
+  int parts_per_cta = 0;    // accumulator blocks per CTA (the warps that own one; 1 when the CTA's warps share a block)
   size_t smem_bytes = 0;
   Act2Layout a2{};
 };

@@ -85,9 +85,9 @@ static Bwd2Launcher pick_backward2(int multi) {
   else return nullptr;
 }
 
-template <int L, int H>
-static cudaError_t launch_backward3(const Bwd3Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st) {
-  auto kern = gns_backward3_kernel<L, H, true>;
+template <int L, int H, int BT, int LT, int TB, int MINB>
+static cudaError_t launch_backward3_g(const Bwd3Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st) {
+  auto kern = gns_backward3_kernel<L, H, BT, LT, TB, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -97,6 +97,18 @@ static cudaError_t launch_backward3(const Bwd3Args& a, const Bwd2Geom& g, int nu
   const int ctas = (int)std::min<long long>(std::min<long long>(a.S, (long long)occ * num_sms), g.ctas);
   kern<<<ctas, g.T, g.smem_bytes, st>>>(a);
   return cudaGetLastError();
+}
+// geometry variants: (1, 2) tiles per warp with up to 640 threads of 96 registers, or up to 256 threads of 128 registers
+// and two CTAs per SM; (2, 3) tiles per warp with up to 320 threads of 168 registers
+template <int L, int H>
+static cudaError_t launch_backward3(const Bwd3Args& a, const Bwd2Geom& g, int num_sms, cudaStream_t st) {
+  if (g.bt == 1 && g.lt == 2) {
+    if (g.T <= 256) return launch_backward3_g<L, H, 1, 2, 256, 2>(a, g, num_sms, st);
+    if (g.T <= 640) return launch_backward3_g<L, H, 1, 2, 640, 1>(a, g, num_sms, st);
+  } else if (g.bt == 2 && g.lt == 3 && g.T <= 320) {
+    return launch_backward3_g<L, H, 2, 3, 320, 1>(a, g, num_sms, st);
+  }
+  return cudaErrorInvalidValue;
 }
 template <int L, int H>
 static Bwd3Launcher pick_backward3(int multi) {

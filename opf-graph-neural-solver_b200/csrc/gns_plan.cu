@@ -208,17 +208,33 @@ Bwd2Geom choose_bwd2(const gns_plan* plan, const ModelDims& md, long long S) {
   const int force = env_int("GNS_BWD2", 0);
   if (S <= 0) return g;
   if (env_int("GNS_BWD3", 0) == 1 && md.multi && md.H == 10 && (md.L == 10 || md.L == 20) && plan->max_walk >= 1) {
-    // fragment-space kernel (gns_backward3.cuh): one thread per bus for the physics, 16-item tiles per warp
-    const int T = std::max(64, ((plan->N + 31) / 32) * 32);
-    const int nw = T / 32;
+    // fragment-space kernel (gns_backward3.cuh): one thread per bus for the physics, 16-item tiles per warp.
+    // Two geometries.  Wide: one bus tile and at most two line tiles per warp (up to 20 warps of 96 registers, or two
+    // CTAs of up to 8 warps and 128 registers per SM); narrow: two bus / three line tiles per warp (up to 10 warps of 168
+    // registers).  Measured on B200, K=4, 16,384 grids, backward pass only: case300 wide 20.0 ms (18.6 ms with shared
+    // accumulator blocks) / narrow 18.5 ms / first kernel 16.7 ms; case118 wide 10.2 ms / narrow 13.7 ms / first kernel
+    // 8.2 ms.  With 19 warps the legacy mma.sync pipe throttles and the CTA barriers take 22 % of the warp time, so the
+    // wide geometry is the default only where it brings a second CTA onto the SM.  GNS_BWD3_TILES=1 / 2 forces one.
+    // GNS_DETERMINISTIC=0: the warps of a CTA share one accumulator block (their reductions race: gradients reproducible
+    // to rounding only); otherwise one block per warp.
     const int nbt = (plan->N + 15) / 16, nlt = (plan->E + 15) / 16;
-    if (T <= 384 && nbt <= 2 * nw && nlt <= 3 * nw && plan->N >= env_int("GNS_BWD2_MIN_SLOTS", 96)) {
+    const int tiles_env = env_int("GNS_BWD3_TILES", 0);
+    const int nw_wide = std::max(std::max(nbt, (nlt + 1) / 2), std::max(2, (plan->N + 31) / 32));
+    const bool wide = tiles_env == 1 || (tiles_env == 0 && nw_wide * 32 <= 256);
+    const int bt = wide ? 1 : 2, lt = wide ? 2 : 3;
+    const int nw = std::max(std::max((nbt + bt - 1) / bt, (nlt + lt - 1) / lt), std::max(2, (plan->N + 31) / 32));
+    const int T = nw * 32;
+    const char* det_env = std::getenv("GNS_DETERMINISTIC");
+    const bool shared_acc = det_env && det_env[0] == '0';
+    if (T <= (wide ? 640 : 320) && plan->N >= env_int("GNS_BWD2_MIN_SLOTS", 96)) {
       g.a2 = make_act2_layout(md.L, md.H, plan->N, plan->Ns, plan->E, plan->max_walk);
       const WLayout W = make_wlayout(md.L, md.H, true);
       const size_t bytes = (size_t)make_bwd3_smem_floats(md.L, md.H, plan->N, plan->E, W.wstep, nw, g.a2) * 4;
       if ((int)bytes <= plan->smem_optin) {
-        g.variant = 3; g.PW = nw; g.CW = nw; g.T = T; g.smem_bytes = bytes;
-        const int per_sm = std::max(1, std::min((int)((size_t)233472 / (bytes + 1024)), 65536 / (T * 168)));
+        g.variant = 3; g.PW = nw; g.CW = shared_acc ? 1 : nw; g.T = T; g.smem_bytes = bytes; g.bt = bt; g.lt = lt;
+        g.parts_per_cta = shared_acc ? 1 : nw;
+        const int regs = !wide ? 168 : (T <= 256 ? 128 : 96);
+        const int per_sm = std::max(1, std::min((int)((size_t)233472 / (bytes + 1024)), 65536 / (T * regs)));
         g.ctas = (int)std::min<long long>(S, (long long)plan->num_sms * per_sm);
         g.ok = true;
         return g;

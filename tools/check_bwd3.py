@@ -49,8 +49,22 @@ def timing(n_bus, S, which):
     os.environ["GNS_BWD2"] = "0"
     src(n_bus, S, "0")
 
+def geometry(n_bus, S=16384, L=20, K=4):
+    """what the library would launch for the backward pass of this case (gns_launch_info)"""
+    buses, lines, gens, _ = pkg.data.make_batch(n_bus, 1, seed=7)
+    model = pkg.GNS(latent_dim=L, hidden_dim=10, K=K, gamma=0.9, multiple_phi=True).cuda()
+    plan = model.plan_for(lines.cuda(), gens.cuda(), n_bus)
+    print(f"    case{n_bus} backward geometry:", plan.launch_info(S, K, L, 10, True, backward=True), flush=True)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "all"
+    for env in ({"GNS_BWD3_TILES": "1"}, {"GNS_BWD3_TILES": "1", "GNS_DETERMINISTIC": "0"}, {"GNS_BWD3_TILES": "2"}) if mode == "geom" else ():
+        os.environ.pop("GNS_DETERMINISTIC", None)
+        os.environ.update(env); setk("3"); print(env); geometry(300); geometry(118)
+    extra = [a for a in sys.argv[2:] if "=" in a]
+    for a in extra:
+        k, v = a.split("=", 1); os.environ[k] = v
     if mode in ("parity", "all"):
         parity(300, 3)
         parity(118, 9)
