@@ -97,6 +97,38 @@ def test_warp_specialised_backward_kernel_matches_oracle(lib, monkeypatch, n_bus
     assert all(torch.equal(runs[0][n], runs[1][n]) for n in runs[0])
 
 
+@pytest.mark.parametrize("tiles", ["1", "2"])
+@pytest.mark.parametrize("n_bus,S,L,K", [(300, 3, 20, 4), (118, 9, 20, 4), (300, 150, 10, 3)])
+def test_fragment_space_backward_kernel_matches_oracle(lib, monkeypatch, n_bus, S, L, K, tiles):
+    """GNS_BWD3=1: the third implementation of the adjoint (every layer of the MLP adjoint as 3xTF32 mma.sync products on
+    16-item tiles, csrc/gns_backward3.cuh), in both launch geometries (GNS_BWD3_TILES=1: one bus tile per warp, 2: two),
+    gives the same gradients, bit-reproducibly."""
+    monkeypatch.setenv("GNS_BWD3", "1")
+    monkeypatch.setenv("GNS_BWD3_TILES", tiles)
+    torch.manual_seed(0)
+    model = pkg.GNS(latent_dim=L, hidden_dim=10, K=K, gamma=0.9, multiple_phi=True).cuda()
+    buses, lines, gens, _ = pkg.data.make_batch(n_bus, S, seed=7)
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    (_, _, otot, _), want = orc.gns_loss_and_grads(params, buses.double(), lines.double(), gens.double(), K=K,
+                                                   latent_dim=L, gamma=0.9, multiple_phi=True)
+    b, l, g = buses.cuda(), lines.cuda(), gens.cuda()
+    info = model.plan_for(l, g, n_bus).launch_info(S, K, L, 10, True, backward=True)
+    assert info["grids_per_cta"] == 1 and info["vector_width"] == 16 * int(tiles), info   # the fragment-space geometry is in use
+    runs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        out = model(b, l, g, *BLG)
+        out[2].mean().backward()
+        runs.append({n: p.grad.detach().clone() for n, p in model.named_parameters()})
+    assert_loss_close(out[2], otot, "total")
+    try:
+        assert_grads_close(runs[0], want, f"case{n_bus} bwd3")
+    except AssertionError:
+        print(per_tensor_report(runs[0], want))
+        raise
+    assert all(torch.equal(runs[0][n], runs[1][n]) for n in runs[0])
+
+
 def test_deepcopied_model_still_receives_gradients(lib):
     """copy.deepcopy drops the flat leaf's hook: the copy must rebuild it instead of training nothing."""
     import copy

@@ -267,8 +267,10 @@ def test_gradient_layout_maps_cover_every_parameter_once(lib, L, multi):
 
 def test_fragment_maps_are_injective(lib):
     """Every packed weight the backward kernels write maps to its own accumulator cell, for both kernels' layouts."""
-    for name in (b"frag", b"frag2"):
+    for name in (b"frag", b"frag2", b"frag3"):
         for multi in (1, 0):
+            if name == b"frag3" and not multi:
+                continue                      # the fragment-space kernel is built for multiple_phi only
             n = lib.gns_layout_export(name, 4, 20, 10, multi, None, 0)
             assert n > 0
             out = np.zeros(n, dtype=np.int32)
@@ -280,6 +282,11 @@ def test_fragment_maps_are_injective(lib):
     lib.gns_layout_export(b"frag", 4, 20, 10, 0, a.ctypes.data, n)
     lib.gns_layout_export(b"frag2", 4, 20, 10, 0, b.ctypes.data, n)
     assert np.array_equal(a >= 0, b >= 0)
+    n3 = lib.gns_layout_export(b"frag3", 4, 20, 10, 1, None, 0)
+    c = np.zeros(n3, dtype=np.int32); a1 = np.zeros(n3, dtype=np.int32)
+    lib.gns_layout_export(b"frag3", 4, 20, 10, 1, c.ctypes.data, n3)
+    lib.gns_layout_export(b"frag", 4, 20, 10, 1, a1.ctypes.data, n3)
+    assert np.array_equal(a1 >= 0, c >= 0)
 
 
 def test_pack_varying_round_trip_and_rejection():
