@@ -101,7 +101,7 @@ struct BwdArgs {
 // The k index of an MMA is a free permutation as long as A and B agree: k slot t (t+4) of MMA i is item
 // 4t+i (16+4t+i), so both fragments come straight from two LDS.128 per row and need no shuffles.
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -512,11 +512,18 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
         // line activations (h1, h2 of one phi evaluation) travel one iteration ahead of their use: the loads of
         // iteration 0 are issued in front of the L-net's first-layer tile, those of it+1 at the top of iteration it
         // (the iteration-major in_pos columns are read once, so there is no L1 reuse to wait for)
-        float nh[2 * H];
+        float nh[H];
+        uint32_t nbits = 0u;          // slope bits of h2
+        const bool quads = a.al.gs != 1;       // grid-major layout: quads of rows (else plain rows)
         auto load_line = [&](const float* actl, int it) {
-          const float* ap = actl + (int)t_inp[(slot_on && it < deg) ? e_in0 + it : 0] * ALS;
+          const int el = (int)t_inp[(slot_on && it < deg) ? e_in0 + it : 0] * ALS + cf * a.al.gl;
+          if (quads) {
+            ldg_rows4<H>(nh, actl, RL, el);
+          } else {
 #pragma unroll
-          for (int o = 0; o < 2 * H; ++o) nh[o] = __ldg(ap + o * RL);
+            for (int o = 0; o < H; ++o) nh[o] = __ldg(actl + o * RL + el);
+          }
+          nbits = __ldg(reinterpret_cast<const uint32_t*>(actl + H * RL) + el);
         };
         // adjoint of one phi net given adjA: line loop, dW2 / db2 / dW1f, adjP, dW1m / db1, adj m
         auto phi_backward = [&](const float* wphi, float* gphi, const float* actl) {
@@ -531,15 +538,16 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             const bool live = slot_on && (it < deg);
             const float* wp = wphi + opaque_zero();
             const int e = live ? e_in0 + it : 0;                 // position in the in-list
-            float h1[H], h2[H], d2[H][1], d1[H], feat[5];
+            float h1[H], d2[H][1], d1[H], feat[5];
 #pragma unroll
-            for (int o = 0; o < H; ++o) { h1[o] = nh[o]; h2[o] = nh[H + o]; }   // fetched one iteration ahead
+            for (int o = 0; o < H; ++o) h1[o] = nh[o];                          // fetched one iteration ahead
+            const uint32_t h2bits = nbits;
             if (it + 1 < warp_max_deg) load_line(actl, it + 1);
             const float* lf = s_linef + (int)t_ini[e] * G + gq;
 #pragma unroll
             for (int c = 0; c < 5; ++c) feat[c] = lf[c * EG];
 #pragma unroll
-            for (int o = 0; o < H; ++o) d2[o][0] = live ? adjA[o] * lrelu_grad(h2[o]) : 0.f;
+            for (int o = 0; o < H; ++o) d2[o][0] = live ? adjA[o] * (((h2bits >> o) & 1u) ? 1.f : kSlope) : 0.f;
 #pragma unroll
             for (int j = 0; j < H; ++j) {
               float t[1] = {0.f};
@@ -610,10 +618,19 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           // ---- activations of this bus and pair kept by the forward kernel: A, h1, h2 of the L-net ----
           float h1L[H], h2L[H];
           {
-            const float* ab = act_k + (size_t)(q * 3 * H) * RB + (size_t)cf * a.al.gs + (size_t)n * AIS;
+            const float* ab = act_k + (size_t)(q * 3 * H) * RB;
+            const int eb = cf * a.al.gs + n * AIS;
             float Aq[H];
+            if (quads) {
+              ldg_rows4<H>(Aq, ab, RB, eb);
+              ldg_rows4<H>(h1L, ab + H * RB, RB, eb);
+              ldg_rows4<H>(h2L, ab + 2 * H * RB, RB, eb);
+            } else {
 #pragma unroll
-            for (int o = 0; o < H; ++o) { Aq[o] = __ldg(ab + o * RB); h1L[o] = __ldg(ab + (H + o) * RB); h2L[o] = __ldg(ab + (2 * H + o) * RB); }
+              for (int o = 0; o < H; ++o) {
+                Aq[o] = __ldg(ab + o * RB + eb); h1L[o] = __ldg(ab + (H + o) * RB + eb); h2L[o] = __ldg(ab + (2 * H + o) * RB + eb);
+              }
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < H; ++j) stage(T_S, j, Aq[j]);        // wide rows of dM
@@ -670,7 +687,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll
           for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, d1[o][0]);
           __syncwarp();
-          const float* const actl = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * RL + (size_t)cf * a.al.gl;
+          const float* const actl = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * (H + 1)) * RL;
           if ((MULTI || qq == 2) && warp_max_deg > 0) load_line(actl, 0);
           // rows: state (4+L, in place), A (H) and deg (1) from the tile, ones -> dW1[:4+L], dM, dc, db1
           tile_gemm_r<H, 4 + L + H + 2>(

@@ -147,7 +147,11 @@ __host__ __device__ constexpr int frag_index(int r, int c) {
 //               a 128-byte multiple.  The forward kernel pays one 32-bit store per grid instead of a vector store.
 //   interleaved [row][item][grid]  when several grids share a CTA (small grids): the lanes of both kernels are
 //               (item, grid) pairs with the grid index fastest, exactly this order.
-// Address of (row, item, grid): row * rb + item * is + grid * gs   (bus block; rl / ls / gl for the line block).
+// Element of (item, grid): item * is + grid * gs (bus block; ls / gl for the line block); an array of H rows takes H * rb
+// floats (rl for the line block).  Grid-major: ordered as quads of rows over the elements (stg_rows4 / ldg_rows4);
+// interleaved: plain rows, (row, element) at row * rb + element (a thread's VG grids are adjacent: one vector store per
+// row).  The line block holds, per phi net, h1 (H rows) and ONE row of words with the LeakyReLU slope bits of h2 (bit o:
+// h2[o] > 0) - the backward pass needs h2 only for its slope.
 struct ActLayout { int rb, is, gs, rl, ls, gl, line_off, total; };
 __host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, int E, int G, bool grid_major) {
   ActLayout a{};
@@ -160,7 +164,7 @@ __host__ __device__ inline ActLayout make_act_layout(int H, int nphi, int Ns, in
     a.rl = pad4(E * G); a.ls = G; a.gl = 1;
   }
   a.line_off = 3 * 3 * H * a.rb;
-  a.total = a.line_off + nphi * 2 * H * a.rl;
+  a.total = a.line_off + nphi * (H + 1) * a.rl;      // per phi net: h1 (H rows) and one row of h2 slope bits
   return a;
 }
 
@@ -325,6 +329,37 @@ template <int N, int VG, bool INTER> __device__ __forceinline__ void stg_rows(fl
     else stg_grids<VG>(p, gstride, x[o]);
     p += rstride;
   }
+}
+
+// Activation arrays of the first backward kernel (ActLayout): the H rows of one hidden vector are kept as QUADS of rows,
+// [element][4] for rows 4c..4c+3 at arr + 4 c rb and [element][2] for the last two rows (H = 10) at arr + (H-2) rb, with
+// element = item * is + grid * gs.  A thread writes / reads a vector with H/4 128-bit and one 64-bit access instead of H
+// 32-bit ones, and the lanes of a warp (consecutive elements) still cover consecutive addresses.
+template <int H, int VG>
+__device__ __forceinline__ void stg_rows4(float* arr, int rb, int e0, int gs, const float (&x)[H][VG]) {
+  static_assert(H % 4 == 2, "quads of rows plus one pair");
+#pragma unroll
+  for (int g = 0; g < VG; ++g) {
+    const int e = e0 + g * gs;
+    float* p = arr + 4 * e;
+#pragma unroll
+    for (int c = 0; c < H / 4; ++c) {
+      __stcs(reinterpret_cast<float4*>(p), make_float4(x[4 * c][g], x[4 * c + 1][g], x[4 * c + 2][g], x[4 * c + 3][g]));
+      p += 4 * rb;
+    }
+    __stcs(reinterpret_cast<float2*>(arr + (size_t)(H - 2) * rb + 2 * e), make_float2(x[H - 2][g], x[H - 1][g]));
+  }
+}
+template <int H>
+__device__ __forceinline__ void ldg_rows4(float* x /* [H] */, const float* arr, size_t rb, int e) {
+  static_assert(H % 4 == 2, "quads of rows plus one pair");
+#pragma unroll
+  for (int c = 0; c < H / 4; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(arr + 4 * c * rb + 4 * (size_t)e));
+    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+  }
+  const float2 v = __ldg(reinterpret_cast<const float2*>(arr + (H - 2) * rb + 2 * (size_t)e));
+  x[H - 2] = v.x; x[H - 1] = v.y;
 }
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }

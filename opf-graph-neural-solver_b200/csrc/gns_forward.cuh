@@ -452,9 +452,17 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
               } else if constexpr (GRAD) {
                 // (the opaque zero keeps the 2H row offsets from being hoisted out of the line loop into spills)
                 const int rl = a.al.rl + opaque_zero();
-                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * 2 * H) * rl + gcol * a.al.gl + (int)t_inp[e] * a.al.ls;
-                stg_rows<H, VG, INTER>(ap, rl, a.al.gl, z);
-                stg_rows<H, VG, INTER>(ap + H * rl, rl, a.al.gl, z2);
+                float* ap = act_k + a.al.line_off + (size_t)((MULTI ? q : 0) * (H + 1)) * rl;
+                const int el = gcol * a.al.gl + (int)t_inp[e] * a.al.ls;
+                if constexpr (INTER) stg_rows<H, VG, true>(ap + el, rl, a.al.gl, z);
+                else stg_rows4<H, VG>(ap, rl, el, a.al.gl, z);
+                uint32_t wb[VG];
+#pragma unroll
+                for (int g = 0; g < VG; ++g) wb[g] = 0u;
+                slope_bits<H, VG>(wb, z2, 0);
+                uint32_t* mp = reinterpret_cast<uint32_t*>(ap + H * rl) + el;
+#pragma unroll
+                for (int g = 0; g < VG; ++g) __stcs(mp + g * a.al.gl, wb[g]);
               }
             }
            }
@@ -472,11 +480,13 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
             }
           }
           if (!prim) continue;
-          float* const ab = (GRAD && !V3) ? act_k + (size_t)(q * 3 * H) * a.al.rb + gcol * a.al.gs + n * a.al.is : nullptr;
+          float* const ab = (GRAD && !V3) ? act_k + (size_t)(q * 3 * H) * a.al.rb : nullptr;   // arrays A, h1L, h2L of the pair
+          const int eb = (GRAD && !V3) ? gcol * a.al.gs + n * a.al.is : 0;                      // this thread's first element
           if constexpr (V3) {
             stg_rows<H, VG, false>(act_k + a.a2.A[q] + my_brank, a.a2.NbP, gstr2, A);
           } else if constexpr (GRAD) {
-            stg_rows<H, VG, INTER>(ab, a.al.rb, a.al.gs, A);
+            if constexpr (INTER) stg_rows<H, VG, true>(ab + eb, a.al.rb, a.al.gs, A);
+            else stg_rows4<H, VG>(ab, a.al.rb, eb, a.al.gs, A);
           }
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;   // L_v, L_theta, L_m are consecutive
           float zL[H][VG];
@@ -546,8 +556,13 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
 #pragma unroll
             for (int g = 0; g < VG; ++g) __stcs(mp + (size_t)g * gstr2, wb[g]);
           } else if constexpr (GRAD) {
-            stg_rows<H, VG, INTER>(ab + H * a.al.rb, a.al.rb, a.al.gs, zL);
-            stg_rows<H, VG, INTER>(ab + 2 * H * a.al.rb, a.al.rb, a.al.gs, z2);
+            if constexpr (INTER) {
+              stg_rows<H, VG, true>(ab + H * a.al.rb + eb, a.al.rb, a.al.gs, zL);
+              stg_rows<H, VG, true>(ab + 2 * H * a.al.rb + eb, a.al.rb, a.al.gs, z2);
+            } else {
+              stg_rows4<H, VG>(ab + H * a.al.rb, a.al.rb, eb, a.al.gs, zL);
+              stg_rows4<H, VG>(ab + 2 * H * a.al.rb, a.al.rb, eb, a.al.gs, z2);
+            }
           }
           if (q < 2) {
             float out[VG];
