@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
 #pragma unroll 1
         for (int qq = 0; qq < 3; ++qq) {
           const int q = (qq == 0) ? 2 : qq - 1;      // m-net first: it reads adj m' before anyone adds to it
+          if (q == 2 && k == K - 1) continue;        // the last step's m net is dead (adj m' = 0; the forward skips it too)
           const float* wphi = s_w + (MULTI ? q * W.phi_size : 0);
           const float* wln = s_w + W.off_ln[0] + q * W.ln_size_s;
           float* gphi = gk + (MULTI ? q * FL.net : 0);   // accumulator blocks of this pair (fragment order)

@@ -381,6 +381,10 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         float A[H][VG];
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
+          // The m net of the LAST step only updates the latent, which nothing reads afterwards (the outputs are v, theta
+          // and the physics losses; ref GNS/main.py:176-202 evaluates it and drops the result, its parameters get no
+          // gradient): dead work, skipped.  (GRADV = 3 keeps it: the two experimental backward kernels walk every pair.)
+          if (!V3 && q == 2 && k == K - 1) break;
           if (MULTI || q == 0) {
 #pragma unroll
             for (int o = 0; o < H; ++o)
