@@ -118,8 +118,10 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {   // fi
 // gfrag: this call's block of the warp-private accumulator (FragLayout); only this warp ever adds to it,
 // in program order, so the reductions are deterministic.
 // CG: the wide rows live in global memory that this kernel updates with reductions: read them from L2 (ld.global.cg)
+// Tiles [skip0, skip1) are left out (their wide rows are known to be all zeros: the latent entering step 0).
 template <int C, int R, bool CG, class RowFn>
-__device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
+__device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag,
+                                              int skip0 = 0, int skip1 = 0) {
   static_assert(C <= 11, "hidden columns 11..15 of the m16 tile are not stored");
   const int lane = threadIdx.x & 31, gi = lane >> 2, t = lane & 3;
   // A fragments of the four MMAs: MMA m covers items a(t, m) = 16 (m / 2) + 4 t + 2 (m % 2) and a + 1
@@ -157,6 +159,9 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
 #pragma unroll UNR
   for (int nt = 0; nt < NT; ++nt) {
     float4 blo, bhi;
+    if constexpr (UNR != 1) {
+      if (nt >= skip0 && nt < skip1) continue;
+    }
     if constexpr (UNR == 1) {
       blo = nlo; bhi = nhi;
       if (nt + 1 < NT) load_b(nt + 1, nlo, nhi);
@@ -196,8 +201,9 @@ __device__ __forceinline__ void tile_gemm_mma(RowFn rowfn, const float* __restri
 // one weight-gradient GEMM call: rows r < R (wide side) x C hidden columns over the warp's 32 items, added
 // into the call's accumulator block
 template <int C, int R, bool CG = false, class RowFn>
-__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag) {
-  tile_gemm_mma<C, R, CG>(rowfn, hidblk, gfrag);
+__device__ __forceinline__ void tile_gemm_r(RowFn rowfn, const float* __restrict__ hidblk, float* __restrict__ gfrag,
+                                            int skip0 = 0, int skip1 = 0) {
+  tile_gemm_mma<C, R, CG>(rowfn, hidblk, gfrag, skip0, skip1);
 }
 
 // Large latent dimensions (L > 32): state m and its adjoint (2 x L x Ns floats, 183 KB for L=64 on
@@ -585,15 +591,19 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           for (int o = 0; o < H; ++o) stage_hid(T_HIDA, o, adjP[o]);
           __syncwarp();
           // dW1m^T[i][o] += m[i] adjP[o];  db1[o] += adjP[o]
-          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * MS : tile + T_ONES; }, tile + T_HIDA, gphi + FL.w1m);
+          // (step 0: the latent rows are zeros, ref GNS/main.py:152 - the tiles made of them only add zeros)
+          tile_gemm_r<H, L + 1>([&](int r) { return r < L ? rows_m + r * MS : tile + T_ONES; }, tile + T_HIDA, gphi + FL.w1m, 0,
+                                k == 0 ? L / 8 : 0);
           {
             float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
             if constexpr (AMREG) {
+              if (k > 0) {       // (the adjoint of the zero latent entering step 0 is not needed)
 #pragma unroll
-              for (int i = 0; i < L; ++i) {
-                float t[1] = {amr[i]};
-                row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
-                amr[i] = t[0];
+                for (int i = 0; i < L; ++i) {
+                  float t[1] = {amr[i]};
+                  row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
+                  amr[i] = t[0];
+                }
               }
             } else {
 #pragma unroll 4
@@ -697,7 +707,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
                        : r < 4 + L ? rows_m + (r - 4) * MS
                                  : (r < 4 + L + H + 1 ? tile + T_S + (r - 4 - L) * kTS : tile + T_ONES);
               },
-              tile + T_HIDA, gln + FL.w1);
+              tile + T_HIDA, gln + FL.w1, 1, k == 0 ? (4 + L) / 8 : 0);      // (step 0: tiles of zero latent rows left out)
           __syncwarp();
           // ---- dX of the first layer ----
 #pragma unroll
@@ -707,11 +717,13 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             adj4[i] += t[0];
           }
           if constexpr (AMREG) {
+            if (k > 0) {
 #pragma unroll
-            for (int i = 0; i < L; ++i) {
-              float t[1] = {amr[i]};
-              row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
-              amr[i] = t[0];
+              for (int i = 0; i < L; ++i) {
+                float t[1] = {amr[i]};
+                row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
+                amr[i] = t[0];
+              }
             }
           } else {
 #pragma unroll 4
