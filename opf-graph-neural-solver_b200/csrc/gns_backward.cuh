@@ -597,13 +597,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
           {
             float (&pv)[H][1] = reinterpret_cast<float (&)[H][1]>(adjP);
             if constexpr (AMREG) {
-              if (k > 0) {       // (the adjoint of the zero latent entering step 0 is not needed)
 #pragma unroll
-                for (int i = 0; i < L; ++i) {
-                  float t[1] = {amr[i]};
-                  row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
-                  amr[i] = t[0];
-                }
+              for (int i = 0; i < L; ++i) {
+                float t[1] = {amr[i]};
+                row_dot<H, HP, 1>(t, pv, wphi + W.phi_w1m + i * HP);
+                amr[i] = t[0];
               }
             } else {
 #pragma unroll 4
@@ -717,13 +715,11 @@ __global__ void __launch_bounds__(TMAX, 1) gns_backward_kernel(const BwdArgs a) 
             adj4[i] += t[0];
           }
           if constexpr (AMREG) {
-            if (k > 0) {
 #pragma unroll
-              for (int i = 0; i < L; ++i) {
-                float t[1] = {amr[i]};
-                row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
-                amr[i] = t[0];
-              }
+            for (int i = 0; i < L; ++i) {
+              float t[1] = {amr[i]};
+              row_dot<H, HP, 1>(t, d1, wln + W.ln_w1 + (4 + i) * HP);
+              amr[i] = t[0];
             }
           } else {
 #pragma unroll 4
