@@ -531,6 +531,9 @@ def run_ours(args):
                      "peak_source": "measured here: max of the register-only FFMA and packed FFMA2 probes "
                                     "(MEASURED_PEAKS.json has no FP32 entry); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
                      "kernel_ms": kern_ms, "flop_per_grid": fl,
+                     "flop_note": "flop_per_grid is the reference's algorithmic MLP count (SURVEY.md 8a/8d); the kernels execute "
+                                  "0.62 of those MACs on case300 K=4 (0.68 before the dead net was dropped): fused W4^T.W1 block, receiver latent hoisted out of the line loop, and "
+                                  "the last step's m net (its result is never read, ref main.py:176-202) is not evaluated",
                      "hbm": {"achieved_gbs": S * (in_b + out_b) / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "frac": S * (in_b + out_b) / (kern_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured"}},
         "strong": strong,
