@@ -1,7 +1,7 @@
 """The five BASELINE.json configurations on one GPU (device-resident inputs, CUDA events, median of 5)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tools.quick_fwd import run
+from tools.timing import run
 print("configs[0] case14 K=4 L=20 forward, batch 1024"); run(14, 1024)
 print("configs[1] case30 training step, batch 4096"); run(30, 4096, train=True)
 print("configs[2] case118 training step, batch 16384"); run(118, 16384, train=True)

@@ -1,4 +1,4 @@
-"""Scratch timing of the forward kernel (device-resident inputs, CUDA events)."""
+"""Timing of the forward kernel and the training step (device-resident inputs, CUDA events); library of baseline_configs.py."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
