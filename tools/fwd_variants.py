@@ -13,9 +13,11 @@ b, l, g, _ = pkg.data.make_batch(n_bus, base, seed=1)
 rep = (S + base - 1) // base
 b, l, g = (t.repeat(rep, 1, 1)[:S].contiguous().cuda() for t in (b, l, g))
 variants = [{}, {"GNS_FWD_VG": "1", "GNS_FWD_NGQ": "2"}, {"GNS_FWD_VG": "1", "GNS_FWD_NGQ": "1"}, {"GNS_FWD_VG": "2", "GNS_FWD_NGQ": "2"}]
+if os.environ.get("FWD_VARIANTS") == "cap":
+    variants = [{}, {"GNS_NO_TMA": "1"}, {"GNS_DEG_CAP": "2"}, {"GNS_DEG_CAP": "2", "GNS_NO_TMA": "1"}, {"GNS_DEG_CAP": "4"}]
 ref = None
 for env in variants:
-    for k in ("GNS_FWD_VG", "GNS_FWD_NGQ"):
+    for k in ("GNS_FWD_VG", "GNS_FWD_NGQ", "GNS_DEG_CAP", "GNS_NO_TMA"):
         os.environ.pop(k, None)
     os.environ.update(env)
     torch.manual_seed(0)
