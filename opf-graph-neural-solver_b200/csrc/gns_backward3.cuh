@@ -16,9 +16,12 @@
 //     goes bus -> line through a shared-memory block (gather by the line's receiving bus), the pre-activation
 //     adjoint of the phi net's first layer goes line -> bus through another (CSR gather in ascending line order).
 //   * weight gradients: every 16-item tile is one k16 chunk of the long-K scheme of gns_backward2.cuh (hid operand
-//     item-major, wide operand = bulk-copied row blocks of the forward's per-grid checkpoints), accumulated in
-//     registers over the warp's tiles and flushed with one red.global.add.v4 per lane and tile per call.
+//     item-major, wide operand = bulk-copied row blocks of the forward's per-grid checkpoints), flushed per tile
+//     with one red.global.add.v4 per lane and 8-row tile (the phi net's two small matrices accumulate over the warp's
+//     line tiles first).
 // Checkpoint layout: Act2Layout (training forward GRADV = 3).  Physics adjoint: one thread per bus, as before.
+// Measured: it executes as many instructions as the first kernel (hidden_dim 10 pads to 16 on every MMA
+// axis, a FP32-accurate product is three HMMA plus two operand splits) and is 11-25 % slower; opt-in, GNS_BWD3=1.
 #pragma once
 #include "gns_backward2.cuh"
 
