@@ -38,7 +38,7 @@ def load_golden(path):
 def assert_bus_close(got, want, what):
     got, want = got.detach().cpu().double(), want.detach().cpu().double()
     err = (got - want).abs()
-    bound = TOL_BUS * want.abs().clamp_min(1.0)          # rel 1e-4 per bus (abs near zero angles)
+    bound = TOL_BUS * want.abs().clamp_min(1.0)          # TOL_BUS relative per bus (absolute near zero angles)
     assert bool((err <= bound).all()), f"{what}: max err {err.max():.3e}"
 
 
