@@ -137,9 +137,22 @@ class CpuArm:
 
 def run_reference_arm(args):
     """`--impl reference`: rank 0 only; other ranks exit 0 without work."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # the other ranks' interpreter start-up (import torch on a fresh box) must not run under rank 0's clock: meet at
+        # a gloo barrier first, then let them leave
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        dist.barrier()
+        dist.destroy_process_group()
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    workers = os.cpu_count() or 1
+    try:
+        # all host cores the container allows (the GPU arm pins itself to the GPU's NUMA node before it runs this leg as a
+        # child process; the CPU arm gets every core back)
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        workers = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):  # pragma: no cover
+        workers = os.cpu_count() or 1
     sample = max(args.cpu_sample or 256, 256)
     arm = CpuArm(args.case, args.K, args.latent, sample, workers)
     for _ in range(args.warmup):
