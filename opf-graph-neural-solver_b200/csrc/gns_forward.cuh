@@ -772,8 +772,8 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
     // ---------------- outputs ----------------
     if constexpr (V3) {
       ckpt2_store(g0, K);
-    } else if (GRAD) {   // final state (v, theta, dP, dQ are what backward needs; m rides along)
-      const int nst4 = (4 + L) * NG / 4;
+    } else if (GRAD) {   // final state: v, theta, dP, dQ are what the backward pass reads; the latent rows are not stored
+      const int nst4 = 4 * NG / 4;
       float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)((4 + L) * NG));
       const float4* srcs = reinterpret_cast<const float4*>(s_state);
       for (int i = tid; i < nst4; i += T) __stcs(dstg + i, srcs[i]);
