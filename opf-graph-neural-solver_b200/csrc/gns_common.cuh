@@ -335,6 +335,19 @@ template <int N, int VG, bool INTER> __device__ __forceinline__ void stg_rows(fl
 // [element][4] for rows 4c..4c+3 at arr + 4 c rb and [element][2] for the last two rows (H = 10) at arr + (H-2) rb, with
 // element = item * is + grid * gs.  A thread writes / reads a vector with H/4 128-bit and one 64-bit access instead of H
 // 32-bit ones, and the lanes of a warp (consecutive elements) still cover consecutive addresses.
+// checkpoint store policy (A/B knob): 0 = st.global.cs (evict first), 1 = default policy, 3 = diagnostic: no store at all
+#ifndef GNS_STORE_MODE
+#define GNS_STORE_MODE 0
+#endif
+template <class V> __device__ __forceinline__ void ckpt_store(V* p, V v) {
+#if GNS_STORE_MODE == 0
+  __stcs(p, v);
+#elif GNS_STORE_MODE == 1
+  *p = v;
+#else
+  if (reinterpret_cast<size_t>(p) == 1) *p = v;      // keeps the value alive, never stores
+#endif
+}
 template <int H, int VG>
 __device__ __forceinline__ void stg_rows4(float* arr, int rb, int e0, int gs, const float (&x)[H][VG]) {
   static_assert(H % 4 == 2, "quads of rows plus one pair");
@@ -344,10 +357,10 @@ __device__ __forceinline__ void stg_rows4(float* arr, int rb, int e0, int gs, co
     float* p = arr + 4 * e;
 #pragma unroll
     for (int c = 0; c < H / 4; ++c) {
-      __stcs(reinterpret_cast<float4*>(p), make_float4(x[4 * c][g], x[4 * c + 1][g], x[4 * c + 2][g], x[4 * c + 3][g]));
+      ckpt_store(reinterpret_cast<float4*>(p), make_float4(x[4 * c][g], x[4 * c + 1][g], x[4 * c + 2][g], x[4 * c + 3][g]));
       p += 4 * rb;
     }
-    __stcs(reinterpret_cast<float2*>(arr + (size_t)(H - 2) * rb + 2 * e), make_float2(x[H - 2][g], x[H - 1][g]));
+    ckpt_store(reinterpret_cast<float2*>(arr + (size_t)(H - 2) * rb + 2 * e), make_float2(x[H - 2][g], x[H - 1][g]));
   }
 }
 template <int H>

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
         const int nst4 = (4 + L) * NG / 4;
         float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (k - 1)) * (size_t)((4 + L) * NG));
         const float4* srcs = reinterpret_cast<const float4*>(s_state);
-        for (int i = tid; i < nst4; i += T) __stcs(dstg + i, srcs[i]);
+        for (int i = tid; i < nst4; i += T) ckpt_store(dstg + i, srcs[i]);
       }
       __syncthreads();
       // Every thread is past the weight wait, and the other buffer was last read before the barrier
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
                 slope_bits<H, VG>(wb, z2, 0);
                 uint32_t* mp = reinterpret_cast<uint32_t*>(ap + H * rl) + el;
 #pragma unroll
-                for (int g = 0; g < VG; ++g) __stcs(mp + g * a.al.gl, wb[g]);
+                for (int g = 0; g < VG; ++g) ckpt_store(mp + g * a.al.gl, wb[g]);
               }
             }
            }
@@ -776,7 +776,7 @@ __global__ void __launch_bounds__(TMAX, 1) gns_forward_kernel(const FwdArgs a) {
       const int nst4 = 4 * NG / 4;
       float4* dstg = reinterpret_cast<float4*>(a.ckpt + ((size_t)batch * K + (K - 1)) * (size_t)((4 + L) * NG));
       const float4* srcs = reinterpret_cast<const float4*>(s_state);
-      for (int i = tid; i < nst4; i += T) __stcs(dstg + i, srcs[i]);
+      for (int i = tid; i < nst4; i += T) ckpt_store(dstg + i, srcs[i]);
     }
     {
       float l2[2][VG];
